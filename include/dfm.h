@@ -1,0 +1,173 @@
+/*
+ * dfm.h -- C ABI of libdfm.so, the B200 (sm_100a) deformation engine.
+ *
+ * This is the drop-in boundary for the deformation hot path of
+ * ivadomed/multimodal-registration.  The reference reaches that path through the Python
+ * API of voxelmorph / neurite (Keras layers and eager functions on channels-last tensors);
+ * each entry point below names the reference interface it replaces.  Citations are
+ * file:line under the reference checkout; "[UR]" marks interfaces that live in the
+ * un-vendored packages voxelmorph@52dd120f / neurite@c7bb05d5 (reference README.md:35-37)
+ * and are specified in SURVEY.md Appendix A.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller; the library allocates
+ *     nothing and keeps no device state between calls;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no default-stream use -> capturable in CUDA graphs;
+ *   - volumes are fp32 unless stated.  A tensor is either "planar"  [B][C][X][Y][Z]
+ *     or "channels-last" (the reference layout) [B][X][Y][Z][C]; Z is fastest in both.
+ *     `flags` says which (DFM_*_CL bits); a displacement field has C = 3 and component d
+ *     displaces along axis d in voxels of its own grid ('ij' indexing);
+ *   - return value 0 on success, a negative DFM_E* code otherwise; dfm_last_error() gives
+ *     the message for the calling thread.  Nothing aborts or throws across the ABI.
+ */
+#ifndef DFM_H_
+#define DFM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFM_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define DFM_OK 0
+#define DFM_EINVAL (-1)       /* bad shape / argument */
+#define DFM_EALIGN (-2)       /* pointer not aligned as required */
+#define DFM_EUNSUPPORTED (-3) /* valid in the reference but not implemented here */
+#define DFM_ECUDA (-4)        /* CUDA runtime error (message has the detail) */
+
+/* interpolation (interp_method of the reference: 'linear' | 'nearest') */
+#define DFM_LINEAR 0
+#define DFM_NEAREST 1
+
+/* layout flags (bit set = channels-last, clear = planar) */
+#define DFM_FIELD_IN_CL 1u  /* input displacement field(s)            */
+#define DFM_FIELD_OUT_CL 2u /* output displacement field              */
+#define DFM_IMG_CL 4u       /* image / volume, input and output alike */
+#define DFM_LOC_ABSOLUTE 8u /* dfm_warp_fwd: `field` holds absolute sample locations (ne.utils.interpn)
+                               instead of displacements added to the voxel grid */
+
+int dfm_version(void);
+const char *dfm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * SpatialTransformer / vxm.utils.transform / ne.utils.interpn  [UR]
+ *   replaces: vxm.layers.SpatialTransformer (train_synthmorph.py:298),
+ *             vxm.networks.Transform(...).predict (gen_apply_def_field.py:74-76,
+ *             3d_reg.py:331-334,377-380, bids_registration.py:335-338,380-383,
+ *             bids_two_steps_registration.py:338-341,354-355,400-401,444-447,496-499),
+ *             vxm.utils.transform (train_synthmorph.py:67, channel-wise: pass B*C items of
+ *             one channel each).
+ *   out[b,c,p] = interp(img[b,c], p + field[b,:,p]), edge clamp; if has_fill, samples whose
+ *   UNCLIPPED location is outside [0, dim-1] become `fill`.
+ *   img: C channels of (Xi,Yi,Zi); field/out grid: (X,Y,Z).  elem_size: bytes per image
+ *   element -- 4 (fp32) for DFM_LINEAR; 1, 2, 4 or 8 for DFM_NEAREST (values are moved,
+ *   not interpreted; `fill` is then given as raw bits in fill_bits).
+ * ------------------------------------------------------------------------------------- */
+int dfm_warp_fwd(const void *img, const float *field, void *out,
+                 int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z,
+                 int interp, int elem_size, int has_fill, float fill, uint64_t fill_bits,
+                 unsigned flags, void *stream);
+
+/* Backward of the linear warp (TensorFlow autodiff semantics of the reference graph:
+ * floor has zero gradient, clip passes gradient inside [0, max] inclusive).
+ *   gimg   (nullable): [B,C,Xi,Yi,Zi] is ACCUMULATED INTO (caller zeroes it).
+ *   gfield (nullable): [B,3,X,Y,Z] is overwritten.
+ *   replaces: the gradient of `pred` at train_synthmorph.py:298,305-306 (d/dfield only) and
+ *   of the SpatialTransformer inside VxmDense (train_synthmorph.py:296). */
+int dfm_warp_bwd(const float *gout, const float *img, const float *field,
+                 float *gimg, float *gfield,
+                 int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z,
+                 int has_fill, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * out = scale*own + interp(scale*src, p + scale*own)        (3-channel fields)
+ *   src == own : one scaling-and-squaring step of vxm.utils.integrate_vec [UR]
+ *   src != own : vxm.utils.compose([src, own]) [UR]
+ *                (bids_two_steps_registration.py:324,346,369,484)
+ *   src grid (Xs,Ys,Zs); own/out grid (X,Y,Z).  `scale` must be a power of two (1 for
+ *   compose); it folds integrate_vec's  v / 2**nb_steps  into the first step.
+ * ------------------------------------------------------------------------------------- */
+int dfm_field_warp_add(const float *src, const float *own, float *out,
+                       int B, int Xs, int Ys, int Zs, int X, int Y, int Z,
+                       float scale, int interp, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * VecInt(method='ss', int_steps) -> vxm.utils.integrate_vec [UR]
+ *   replaces: the VecInt layer inside VxmDense (3d_reg.py:305, bids_registration.py:311,
+ *   bids_two_steps_registration.py:311,314, train_synthmorph.py:296) and labels_to_image
+ *   (train_synthmorph.py:288-289).
+ *   svf -> out on grid (X,Y,Z), nsteps >= 0.  `work`: caller scratch of
+ *   dfm_vecint_workspace_bytes() bytes (planar fp32).  If save_steps != 0, work receives
+ *   v_0 .. v_{nsteps-1} (the inputs of every step, v_0 = svf / 2**nsteps), which
+ *   dfm_vecint_bwd needs.
+ * ------------------------------------------------------------------------------------- */
+size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nsteps, int save_steps);
+int dfm_vecint_fwd(const float *svf, float *out, float *work,
+                   int B, int X, int Y, int Z, int nsteps, int save_steps,
+                   unsigned flags, void *stream);
+/* gsvf = d loss / d svf given gout = d loss / d out and the saved steps (planar).
+ * `scratch`: 2 * B*3*X*Y*Z floats.  All tensors planar. */
+int dfm_vecint_bwd(const float *gout, const float *saved, float *gsvf, float *scratch,
+                   int B, int X, int Y, int Z, int nsteps, void *stream);
+
+/* One SS step backward: given g = dL/dv' and the step input v (v' = v + interp(v, p+v)),
+ * gv[b,:,p] = scale * ( g + dloc-term ) and the dvol-term is scatter-ADDED into gv
+ * (so gv must not alias g).  Exposed for tests. */
+int dfm_ss_step_bwd(const float *g, const float *v, float *gv,
+                    int B, int X, int Y, int Z, float scale, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RescaleTransform(zoom) -> vxm.utils.rescale_dense_transform -> ne.utils.resize [UR]
+ *   replaces: 3d_reg.py:394, bids_registration.py:398, bids_two_steps_registration.py:515,
+ *   Transform(rescale=scale) at the sites listed under dfm_warp_fwd, RescaleTransform
+ *   inside VxmDense / labels_to_image.
+ *   out[b,c,jx,jy,jz] = post * interp(pre * in[b,c], (cx[jx], cy[jy], cz[jz]))
+ *   cx/cy/cz: DEVICE arrays of Xo/Yo/Zo fp32 sample coordinates on the input grid
+ *   (tf.linspace(0, n_in-1, n_out) in the reference; computed by the host shim so the
+ *   coordinate convention stays a host decision).  factor >= 1: pre = factor, post = 1;
+ *   factor < 1: pre = 1, post = factor.  C channels (3 for a field; any C for ne.utils.resize).
+ * ------------------------------------------------------------------------------------- */
+int dfm_resize_fwd(const float *in, float *out, const float *cx, const float *cy, const float *cz,
+                   int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
+                   float pre, float post, int interp, unsigned flags, void *stream);
+/* Adjoint of the linear dfm_resize_fwd: gin[b,c,i] = pre*post * sum_j W[j,i] gout[b,c,j],
+ * written as a gather (no atomics).  Planar only.
+ * lo/hi: DEVICE int arrays (per axis, length n_in): output index range [lo, hi) whose
+ * interpolation support touches input index i (computed by the host from cx/cy/cz). */
+int dfm_resize_bwd(const float *gout, float *gin, const float *cx, const float *cy, const float *cz,
+                   const int *xlo, const int *xhi, const int *ylo, const int *yhi,
+                   const int *zlo, const int *zhi,
+                   int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
+                   float pre, float post, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Jacobian-determinant map  (eval_reg_with_jacobian.py:62-78)
+ *   field: [3][X][Y][Z] planar or [X][Y][Z][3] channels-last (DFM_FIELD_IN_CL), fp32
+ *          (in_f64 = 0) or fp64 (in_f64 = 1).
+ *   det:   [(X-4)(Y-4)(Z-4)] fp32 (out_f64 = 0) or fp64 (out_f64 = 1); nullable.
+ *   4th-order central differences on the interior, det(I + J), all arithmetic in fp64.
+ *   stats (device, 4 doubles, nullable): n_negative (det < 0), sum(det), sum(det^2), n_total.
+ *   partials: caller scratch of dfm_jacdet_workspace_bytes() bytes.  B fields per call;
+ *   stats is then [B][4].
+ * ------------------------------------------------------------------------------------- */
+size_t dfm_jacdet_workspace_bytes(int B, int X, int Y, int Z);
+int dfm_jacdet(const void *field, void *det, double *stats, void *partials,
+               int B, int X, int Y, int Z, int in_f64, int out_f64,
+               unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout conversion between the reference's channels-last tensors and planar tensors.
+ *   cl [B][N][C]  <->  planar [B][C][N],  elem_size in {1, 2, 4, 8}.
+ * ------------------------------------------------------------------------------------- */
+int dfm_cl_to_planar(const void *cl, void *planar, int B, int C, size_t N, int elem_size, void *stream);
+int dfm_planar_to_cl(const void *planar, void *cl, int B, int C, size_t N, int elem_size, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFM_H_ */

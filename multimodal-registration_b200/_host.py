@@ -1,0 +1,64 @@
+"""Host <-> device plumbing for the Keras-style entry points (numpy in, numpy out).
+
+Inputs are staged through cached PINNED buffers and copied with cudaMemcpyAsync on the current
+stream; results come back through pinned buffers too.  This is the path `bench.py` times as
+`e2e` (host buffers, copies inside the timed region).
+"""
+import numpy as np
+import torch
+
+_PINNED = {}
+
+
+def _pinned(shape, dtype, tag):
+    key = (tuple(shape), dtype, tag)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 64:
+            _PINNED.clear()
+        buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        _PINNED[key] = buf
+    return buf
+
+
+def device():
+    if not torch.cuda.is_available():
+        from ._lib import DfmError
+        raise DfmError('no CUDA device: the deformation engine has no CPU path')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_device(x, dtype=None, tag='in'):
+    """numpy array / CPU tensor / CUDA tensor -> CUDA tensor (optionally cast to dtype)."""
+    dev = device()
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x if dtype is None or x.dtype == dtype else x.to(dtype)
+        t = x
+    else:
+        a = np.asarray(x)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        if a.dtype == np.float64 and dtype == torch.float32:
+            a = a.astype(np.float32)          # Keras casts inputs to floatx on the host too
+        t = torch.from_numpy(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_pinned():
+        stage = _pinned(t.shape, t.dtype, tag)
+        stage.copy_(t)
+        t = stage
+    return t.to(dev, non_blocking=True)
+
+
+def to_host(t, tag='out', copy=True):
+    """CUDA tensor (any physical layout) -> C-contiguous numpy array of its logical shape.
+    copy=False returns a view of the cached pinned staging buffer (valid until the next call
+    that produces an output of the same shape and tag) and saves one host memcpy."""
+    if not t.is_contiguous():
+        from . import ops
+        t = ops.to_layout(t, 'cl')
+    stage = _pinned(t.shape, t.dtype, tag)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage.numpy().copy() if copy else stage.numpy()

@@ -1,0 +1,71 @@
+"""ctypes binding of libdfm.so (the C ABI declared in include/dfm.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdfm.so')
+
+DFM_LINEAR, DFM_NEAREST = 0, 1
+FIELD_IN_CL, FIELD_OUT_CL, IMG_CL, LOC_ABSOLUTE = 1, 2, 4, 8
+
+_c = ctypes
+_p, _i, _f, _u, _z, _u64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_uint, _c.c_size_t, _c.c_uint64
+
+# name -> (restype, argtypes); must list every symbol include/dfm.h declares
+SIGNATURES = {
+    'dfm_version': (_i, []),
+    'dfm_last_error': (_c.c_char_p, []),
+    'dfm_warp_fwd': (_i, [_p, _p, _p] + [_i] * 8 + [_i, _i, _i, _f, _u64, _u, _p]),
+    'dfm_warp_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
+    'dfm_field_warp_add': (_i, [_p, _p, _p] + [_i] * 7 + [_f, _i, _u, _p]),
+    'dfm_vecint_workspace_bytes': (_z, [_i] * 6),
+    'dfm_vecint_fwd': (_i, [_p, _p, _p] + [_i] * 6 + [_u, _p]),
+    'dfm_vecint_bwd': (_i, [_p] * 4 + [_i] * 5 + [_p]),
+    'dfm_ss_step_bwd': (_i, [_p] * 3 + [_i] * 4 + [_f, _p]),
+    'dfm_resize_fwd': (_i, [_p] * 5 + [_i] * 8 + [_f, _f, _i, _u, _p]),
+    'dfm_resize_bwd': (_i, [_p] * 11 + [_i] * 8 + [_f, _f, _p]),
+    'dfm_jacdet_workspace_bytes': (_z, [_i] * 4),
+    'dfm_jacdet': (_i, [_p] * 4 + [_i] * 6 + [_u, _p]),
+    'dfm_cl_to_planar': (_i, [_p, _p, _i, _i, _z, _i, _p]),
+    'dfm_planar_to_cl': (_i, [_p, _p, _i, _i, _z, _i, _p]),
+}
+
+
+class DfmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libdfm.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DfmError(
+            'libdfm.so not found at %s -- build it with `python __graft_entry__.py` or '
+            '`make -C multimodal-registration_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise DfmError with dfm_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise DfmError('%s failed (%d): %s' % (name, rc, lib.dfm_last_error().decode()))
+
+
+def version():
+    return load().dfm_version()

@@ -1,0 +1,422 @@
+"""Device-level deformation ops on torch CUDA tensors, backed by libdfm.so through ctypes.
+
+Tensors keep the reference's LOGICAL shape -- channels-last ``[B, X, Y, Z, C]`` -- while the
+PHYSICAL layout is either contiguous channels-last ("cl") or channel-planar ("planar": the
+storage is ``[B, C, X, Y, Z]`` and the tensor is a permuted view of it).  Kernels prefer
+planar (128-bit coalesced access along z); inputs in either layout are consumed in place and
+the layout bits are passed to the C ABI, so no transposition pass is needed at the boundary.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all voxel work is
+done by the CUDA kernels.  There is no CPU path: CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _coords, _lib
+
+LINEAR, NEAREST = 'linear', 'nearest'
+_INTERP = {LINEAR: _lib.DFM_LINEAR, NEAREST: _lib.DFM_NEAREST}
+
+
+# ---------------------------------------------------------------------------------------
+# layout helpers
+# ---------------------------------------------------------------------------------------
+def _interp_code(interp_method):
+    try:
+        return _INTERP[interp_method]
+    except KeyError:
+        raise ValueError("interp_method must be 'linear' or 'nearest', got %r" % (interp_method,))
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DfmError('%s must be a CUDA tensor: the deformation engine has no CPU path' % name)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _perm_to_planar(nd):
+    # logical [B, s1..sk, C] -> storage order [B, C, s1..sk]
+    return (0, nd - 1) + tuple(range(1, nd - 1))
+
+
+def _perm_to_logical(nd):
+    return (0,) + tuple(range(2, nd)) + (1,)
+
+
+def layout_of(t):
+    """'cl', 'planar', 'both' (one channel, contiguous) or None (needs a copy)."""
+    cl = t.is_contiguous()
+    pl = t.permute(_perm_to_planar(t.dim())).is_contiguous()
+    if cl and pl:
+        return 'both'
+    if cl:
+        return 'cl'
+    if pl:
+        return 'planar'
+    return None
+
+
+def empty(shape, layout, device, dtype=torch.float32):
+    """Uninitialised logical ``shape`` tensor with the given physical layout."""
+    shape = tuple(int(s) for s in shape)
+    if layout == 'cl':
+        return torch.empty(shape, device=device, dtype=dtype)
+    nd = len(shape)
+    storage = torch.empty((shape[0], shape[-1]) + shape[1:-1], device=device, dtype=dtype)
+    return storage.permute(_perm_to_logical(nd))
+
+
+def to_layout(t, layout):
+    """Return ``t`` (logical shape unchanged) in physical layout 'cl' or 'planar' using the
+    library's own transposition kernels; no-op if it already is."""
+    cur = layout_of(t)
+    if cur == 'both' or cur == layout:
+        return t
+    if cur is None:
+        t = t.contiguous()        # odd strides: normalise first (boundary glue, not hot path)
+        if layout == 'cl':
+            return t
+    B, C = t.shape[0], t.shape[-1]
+    N = 1
+    for s in t.shape[1:-1]:
+        N *= int(s)
+    out = empty(t.shape, layout, t.device, t.dtype)
+    fn = 'dfm_cl_to_planar' if layout == 'planar' else 'dfm_planar_to_cl'
+    src, dst = (t, out)
+    _lib.call(fn, _ptr(src), _ptr(dst), B, C, N, t.element_size(), _stream())
+    return out
+
+
+def _field_layout(t, name):
+    """Ensure a 3-channel field is directly consumable; returns (tensor, is_cl)."""
+    lay = layout_of(t)
+    if lay is None:
+        t = t.contiguous()
+        lay = 'cl'
+    return t, lay == 'cl'
+
+
+def _check_field(t, name, nd=5):
+    _require_cuda(t, name)
+    if t.dim() != nd or t.shape[-1] != nd - 2:
+        raise ValueError('%s must be [B, X, Y, Z, 3], got %s' % (name, tuple(t.shape)))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t
+
+
+# ---------------------------------------------------------------------------------------
+# SpatialTransformer / transform
+# ---------------------------------------------------------------------------------------
+def _warp_fwd_raw(img, field, interp, fill_value, loc_absolute=False):
+    B, Xi, Yi, Zi, C = img.shape
+    _, X, Y, Z, _ = field.shape
+    field, f_cl = _field_layout(field, 'field')
+    lay = layout_of(img)
+    if lay is None:
+        img = img.contiguous()
+        lay = 'cl'
+    img_cl = lay == 'cl'
+    out = empty((B, X, Y, Z, C), 'cl' if img_cl else 'planar', img.device, img.dtype)
+    flags = ((_lib.FIELD_IN_CL if f_cl else 0) | (_lib.IMG_CL if img_cl else 0) |
+             (_lib.LOC_ABSOLUTE if loc_absolute else 0))
+    has_fill = fill_value is not None
+    fill_f, fill_bits = 0.0, 0
+    if has_fill:
+        fill_f = float(fill_value)
+        fill_bits = int.from_bytes(torch.tensor([fill_value]).to(img.dtype).numpy().tobytes(), 'little')
+    _lib.call('dfm_warp_fwd', _ptr(img), _ptr(field), _ptr(out), B, C, Xi, Yi, Zi, X, Y, Z,
+              _interp_code(interp), img.element_size(), int(has_fill), fill_f, fill_bits, flags, _stream())
+    return out
+
+
+class _WarpLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, field, fill_value):
+        out = _warp_fwd_raw(img, field, LINEAR, fill_value)
+        ctx.save_for_backward(img, field)
+        ctx.has_fill = fill_value is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, field = ctx.saved_tensors
+        B, Xi, Yi, Zi, C = img.shape
+        _, X, Y, Z, _ = field.shape
+        field, f_cl = _field_layout(field, 'field')
+        lay = layout_of(img)
+        if lay is None:
+            img = img.contiguous()
+            lay = 'cl'
+        img_cl = lay == 'cl'
+        gout = to_layout(gout.float(), 'cl' if img_cl else 'planar')
+        need_img, need_field = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gimg = gfield = None
+        if need_img:
+            gimg = empty(img.shape, 'cl' if img_cl else 'planar', img.device)
+            gimg.zero_()
+        if need_field:
+            gfield = empty(field.shape, 'planar', img.device)
+        flags = (_lib.FIELD_IN_CL if f_cl else 0) | (_lib.IMG_CL if img_cl else 0)
+        _lib.call('dfm_warp_bwd', _ptr(gout), _ptr(img), _ptr(field), _ptr(gimg), _ptr(gfield),
+                  B, C, Xi, Yi, Zi, X, Y, Z, int(ctx.has_fill), flags, _stream())
+        return gimg, gfield, None
+
+
+def warp(img, field, interp_method=LINEAR, fill_value=None, loc_absolute=False):
+    """out[b, p, c] = interp(img[b, ..., c], p + field[b, p, :]).
+
+    img [B, Xi, Yi, Zi, C]; field [B, X, Y, Z, 3] -> [B, X, Y, Z, C].  Mirrors the batched
+    ``vxm.layers.SpatialTransformer`` of the reference (dfm.h: dfm_warp_fwd).
+    loc_absolute: ``field`` holds sample locations themselves (``ne.utils.interpn``; no autograd)."""
+    _require_cuda(img, 'img')
+    field = _check_field(field, 'field')
+    if img.dim() != 5:
+        raise ValueError('img must be [B, X, Y, Z, C], got %s' % (tuple(img.shape),))
+    if img.shape[0] != field.shape[0]:
+        raise ValueError('batch mismatch: img %d vs field %d' % (img.shape[0], field.shape[0]))
+    code = _interp_code(interp_method)
+    if code == _lib.DFM_LINEAR:
+        if img.dtype != torch.float32:
+            img = img.float()
+        if not loc_absolute and torch.is_grad_enabled() and (img.requires_grad or field.requires_grad):
+            return _WarpLinear.apply(img, field, fill_value)
+        return _warp_fwd_raw(img.detach(), field.detach(), LINEAR, fill_value, loc_absolute)
+    if img.element_size() not in (1, 2, 4, 8) or img.dtype == torch.bool:
+        img = img.float()
+    return _warp_fwd_raw(img.detach(), field.detach(), NEAREST, fill_value, loc_absolute)
+
+
+def warp_channelwise(img, field, interp_method=LINEAR, fill_value=None):
+    """Channel-wise transform: field [B, X, Y, Z, C, 3] carries one 3-vector per channel
+    (``vxm.utils.transform`` as called at train_synthmorph.py:67).  Each channel is an
+    independent single-channel warp, so this is the batched kernel over B*C items."""
+    _require_cuda(img, 'img')
+    _require_cuda(field, 'field')
+    B, X, Y, Z, C, D = field.shape
+    if D != 3 or img.shape[-1] != C:
+        raise ValueError('channel-wise field must be [B, X, Y, Z, C, 3] with C == img channels')
+    img_p = to_layout(img, 'planar')                         # storage [B, C, Xi, Yi, Zi]
+    Xi, Yi, Zi = img.shape[1:4]
+    img_items = img_p.permute(0, 4, 1, 2, 3).reshape(B * C, Xi, Yi, Zi, 1)
+    f = to_layout(field.reshape(B, X, Y, Z, C * 3).float(), 'planar')        # [B, C*3, X, Y, Z]
+    f_items = f.permute(0, 4, 1, 2, 3).reshape(B * C, 3, X, Y, Z).permute(0, 2, 3, 4, 1)
+    out = warp(img_items, f_items, interp_method, fill_value)               # [B*C, X, Y, Z, 1]
+    return out.reshape(B, C, X, Y, Z).permute(0, 2, 3, 4, 1)
+
+
+# ---------------------------------------------------------------------------------------
+# field self/cross warps: SS step, compose, VecInt
+# ---------------------------------------------------------------------------------------
+def _field_warp_add_raw(src, own, scale, interp, out_layout='planar'):
+    B, X, Y, Z, _ = own.shape
+    _, Xs, Ys, Zs, _ = src.shape
+    own, own_cl = _field_layout(own, 'own')
+    if src is not own:
+        src = to_layout(src, 'cl' if own_cl else 'planar')
+    else:
+        src = own
+    out = empty(own.shape, out_layout, own.device)
+    flags = (_lib.FIELD_IN_CL if own_cl else 0) | (_lib.FIELD_OUT_CL if out_layout == 'cl' else 0)
+    _lib.call('dfm_field_warp_add', _ptr(src), _ptr(own), _ptr(out), B, Xs, Ys, Zs, X, Y, Z,
+              float(scale), _interp_code(interp), flags, _stream())
+    return out
+
+
+class _Compose2(torch.autograd.Function):
+    """out = own + interp(src, p + own)  (linear)."""
+
+    @staticmethod
+    def forward(ctx, src, own):
+        ctx.save_for_backward(src, own)
+        return _field_warp_add_raw(src, own, 1.0, LINEAR)
+
+    @staticmethod
+    def backward(ctx, gout):
+        src, own = ctx.saved_tensors
+        B, Xs, Ys, Zs, _ = src.shape
+        _, X, Y, Z, _ = own.shape
+        gout = to_layout(gout.float(), 'planar')
+        src_p, own_p = to_layout(src, 'planar'), to_layout(own, 'planar')
+        gsrc = empty(src.shape, 'planar', src.device)
+        gsrc.zero_()
+        gloc = empty(own.shape, 'planar', own.device)
+        _lib.call('dfm_warp_bwd', _ptr(gout), _ptr(src_p), _ptr(own_p), _ptr(gsrc), _ptr(gloc),
+                  B, 3, Xs, Ys, Zs, X, Y, Z, 0, 0, _stream())
+        return gsrc, gout + gloc
+
+
+def compose(transforms, interp_method=LINEAR, out_layout='planar'):
+    """vxm.utils.compose for dense shifts: right fold ``curr = curr + transform(nxt, curr)``
+    (bids_two_steps_registration.py:324,346,369,484).  Batched ``[B, X, Y, Z, 3]`` fields."""
+    if len(transforms) < 2:
+        raise ValueError('Compose transform list size must be greater than 1')
+    curr = _check_field(transforms[-1], 'transforms[-1]')
+    rest = list(reversed(transforms[:-1]))
+    for n, nxt in enumerate(rest):
+        nxt = _check_field(nxt, 'transforms[%d]' % (len(rest) - 1 - n))
+        lay = out_layout if n == len(rest) - 1 else 'planar'
+        if interp_method == LINEAR and torch.is_grad_enabled() and (nxt.requires_grad or curr.requires_grad):
+            curr = _Compose2.apply(nxt, curr)
+            if lay == 'cl':
+                curr = to_layout(curr, 'cl')
+        else:
+            curr = _field_warp_add_raw(nxt, curr, 1.0, interp_method, lay)
+    return curr
+
+
+def _vecint_raw(svf, nsteps, save_steps, out_layout):
+    B, X, Y, Z, _ = svf.shape
+    svf, in_cl = _field_layout(svf, 'svf')
+    out = empty(svf.shape, out_layout, svf.device)
+    nbytes = _lib.load().dfm_vecint_workspace_bytes(B, X, Y, Z, nsteps, int(save_steps))
+    work = torch.empty(max(nbytes // 4, 1), device=svf.device, dtype=torch.float32)
+    flags = (_lib.FIELD_IN_CL if in_cl else 0) | (_lib.FIELD_OUT_CL if out_layout == 'cl' else 0)
+    _lib.call('dfm_vecint_fwd', _ptr(svf), _ptr(out), _ptr(work), B, X, Y, Z, nsteps, int(save_steps),
+              flags, _stream())
+    return out, work
+
+
+class _VecInt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, svf, nsteps):
+        out, work = _vecint_raw(svf, nsteps, True, 'planar')
+        ctx.save_for_backward(work)
+        ctx.nsteps = nsteps
+        ctx.shape = tuple(svf.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (saved,) = ctx.saved_tensors
+        B, X, Y, Z, _ = ctx.shape
+        gout = to_layout(gout.float(), 'planar')
+        if gout.data_ptr() % 16:
+            gout = gout.clone(memory_format=torch.preserve_format)
+        gsvf = empty(ctx.shape, 'planar', gout.device)
+        n = B * 3 * X * Y * Z
+        scratch = torch.empty(2 * n, device=gout.device, dtype=torch.float32)
+        _lib.call('dfm_vecint_bwd', _ptr(gout), _ptr(saved), _ptr(gsvf), _ptr(scratch), B, X, Y, Z,
+                  ctx.nsteps, _stream())
+        return gsvf, None
+
+
+def vecint(svf, nsteps=7, out_layout='planar'):
+    """Scaling and squaring: ``v = svf / 2**n; n times v = v + interp(v, p + v)``.
+    Mirrors vxm.layers.VecInt(method='ss', int_steps=nsteps) (dfm.h: dfm_vecint_fwd)."""
+    svf = _check_field(svf, 'svf')
+    nsteps = int(nsteps)
+    if nsteps < 0:
+        raise ValueError('nb_steps should be >= 0, found: %d' % nsteps)
+    if torch.is_grad_enabled() and svf.requires_grad:
+        out = _VecInt.apply(svf, nsteps)
+        return to_layout(out, 'cl') if out_layout == 'cl' else out
+    return _vecint_raw(svf, nsteps, False, out_layout)[0]
+
+
+# ---------------------------------------------------------------------------------------
+# resize / rescale
+# ---------------------------------------------------------------------------------------
+def _resize_raw(vol, out_shape, pre, post, interp, out_layout):
+    B, Xi, Yi, Zi, C = vol.shape
+    Xo, Yo, Zo = out_shape
+    lay = layout_of(vol)
+    if lay is None:
+        vol = vol.contiguous()
+        lay = 'cl'
+    in_cl = lay == 'cl'
+    dev = vol.device.index if vol.device.index is not None else torch.cuda.current_device()
+    cx = _coords.device_tables(Xi, Xo, dev)[0]
+    cy = _coords.device_tables(Yi, Yo, dev)[0]
+    cz = _coords.device_tables(Zi, Zo, dev)[0]
+    out = empty((B, Xo, Yo, Zo, C), out_layout, vol.device)
+    flags = (_lib.FIELD_IN_CL if in_cl else 0) | (_lib.FIELD_OUT_CL if out_layout == 'cl' else 0)
+    _lib.call('dfm_resize_fwd', _ptr(vol), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), B, C, Xi, Yi, Zi,
+              Xo, Yo, Zo, float(pre), float(post), _interp_code(interp), flags, _stream())
+    return out
+
+
+class _ResizeLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vol, out_shape, pre, post):
+        ctx.in_shape = tuple(vol.shape)
+        ctx.out_shape = tuple(out_shape)
+        ctx.pre, ctx.post = pre, post
+        return _resize_raw(vol, out_shape, pre, post, LINEAR, 'planar')
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, Xi, Yi, Zi, C = ctx.in_shape
+        Xo, Yo, Zo = ctx.out_shape
+        gout = to_layout(gout.float(), 'planar')
+        dev = gout.device.index
+        tx, ty, tz = (_coords.device_tables(Xi, Xo, dev), _coords.device_tables(Yi, Yo, dev),
+                      _coords.device_tables(Zi, Zo, dev))
+        gin = empty(ctx.in_shape, 'planar', gout.device)
+        _lib.call('dfm_resize_bwd', _ptr(gout), _ptr(gin), _ptr(tx[0]), _ptr(ty[0]), _ptr(tz[0]),
+                  _ptr(tx[1]), _ptr(tx[2]), _ptr(ty[1]), _ptr(ty[2]), _ptr(tz[1]), _ptr(tz[2]),
+                  B, C, Xi, Yi, Zi, Xo, Yo, Zo, float(ctx.pre), float(ctx.post), _stream())
+        return gin, None, None, None
+
+
+def resize(vol, zoom_factor, interp_method=LINEAR, pre=1.0, post=1.0, out_layout='planar'):
+    """ne.utils.resize on a batched ``[B, X, Y, Z, C]`` volume: corner-aligned resample onto
+    ``linspace(0, n-1, int(n*zoom))`` per axis; out = post * interp(pre * vol)."""
+    _require_cuda(vol, 'vol')
+    if vol.dim() != 5:
+        raise ValueError('vol must be [B, X, Y, Z, C], got %s' % (tuple(vol.shape),))
+    if vol.dtype != torch.float32:
+        vol = vol.float()
+    zoom = list(zoom_factor) if isinstance(zoom_factor, (list, tuple)) else [zoom_factor] * 3
+    out_shape = tuple(int(vol.shape[1 + d] * zoom[d]) for d in range(3))
+    if _interp_code(interp_method) == _lib.DFM_LINEAR and torch.is_grad_enabled() and vol.requires_grad:
+        out = _ResizeLinear.apply(vol, out_shape, float(pre), float(post))
+        return to_layout(out, 'cl') if out_layout == 'cl' else out
+    return _resize_raw(vol, out_shape, pre, post, interp_method, out_layout)
+
+
+def rescale_dense_transform(trf, factor, interp_method=LINEAR, out_layout='planar'):
+    """vxm.utils.rescale_dense_transform on batched fields: factor < 1 resizes then scales the
+    vectors, factor >= 1 scales then resizes (3d_reg.py:394, bids_registration.py:398,
+    bids_two_steps_registration.py:515)."""
+    trf = _check_field(trf, 'transform')
+    if factor < 1:
+        return resize(trf, factor, interp_method, pre=1.0, post=factor, out_layout=out_layout)
+    return resize(trf, factor, interp_method, pre=factor, post=1.0, out_layout=out_layout)
+
+
+# ---------------------------------------------------------------------------------------
+# Jacobian determinant
+# ---------------------------------------------------------------------------------------
+def jacobian_determinant(field, out_dtype=torch.float64, want_det=True, want_stats=True):
+    """det(I + grad u) on the interior [2:-2]^3 with 4th-order central differences, and the
+    statistics of eval_reg_with_jacobian.py:62-91.
+
+    field: [B, X, Y, Z, 3] (fp32 or fp64, either physical layout).
+    Returns (det [B, X-4, Y-4, Z-4] or None, stats [B, 4] float64 = n_negative, sum, sum of
+    squares, n_total; or None)."""
+    _require_cuda(field, 'field')
+    if field.dim() != 5 or field.shape[-1] != 3:
+        raise ValueError('field must be [B, X, Y, Z, 3], got %s' % (tuple(field.shape),))
+    if field.dtype not in (torch.float32, torch.float64):
+        field = field.float()
+    B, X, Y, Z, _ = field.shape
+    field, f_cl = _field_layout(field, 'field')
+    det = torch.empty((B, X - 4, Y - 4, Z - 4), device=field.device, dtype=out_dtype) if want_det else None
+    stats = part = None
+    if want_stats:
+        stats = torch.empty((B, 4), device=field.device, dtype=torch.float64)
+        nbytes = _lib.load().dfm_jacdet_workspace_bytes(B, X, Y, Z)
+        part = torch.empty(max(nbytes // 8, 1), device=field.device, dtype=torch.float64)
+    _lib.call('dfm_jacdet', _ptr(field), _ptr(det), _ptr(stats), _ptr(part), B, X, Y, Z,
+              int(field.dtype == torch.float64), int(out_dtype == torch.float64),
+              _lib.FIELD_IN_CL if f_cl else 0, _stream())
+    return det, stats

@@ -1,0 +1,125 @@
+"""vxm.networks mirror: Transform and the deformation tail of VxmDense.
+
+``predict`` follows Keras: numpy (host) inputs in, numpy out; ``__call__`` keeps tensors on
+the device.  Host inputs go through pinned staging buffers (see ``_host``).
+"""
+import types
+
+import numpy as np
+import torch
+
+from .. import _host, ops
+from . import layers
+
+
+class Transform(torch.nn.Module):
+    """[scan, trf] -> RescaleTransform(rescale)? -> SpatialTransformer
+    (gen_apply_def_field.py:74-76, 3d_reg.py:331-334,377-380, bids_*.py)."""
+
+    def __init__(self, inshape, affine=False, interp_method='linear', rescale=None,
+                 fill_value=None, nb_feats=1):
+        super().__init__()
+        if affine:
+            raise NotImplementedError('Transform(affine=True) is not on the reference hot path')
+        self.inshape = tuple(int(d) for d in inshape)
+        if len(self.inshape) != 3:
+            raise NotImplementedError('Transform: only 3-D volumes are supported')
+        self.nb_feats = nb_feats
+        self.rescale = rescale
+        self.trf_shape = self.inshape if rescale is None else tuple(int(d / rescale) for d in self.inshape)
+        self.rescaler = layers.RescaleTransform(rescale) if rescale is not None else None
+        self.transformer = layers.SpatialTransformer(interp_method=interp_method, fill_value=fill_value)
+
+    def _check(self, scan, trf):
+        if tuple(scan.shape[1:]) != self.inshape + (self.nb_feats,):
+            raise ValueError('Transform: scan input has shape %s, expected [B, %s]'
+                             % (tuple(scan.shape), ', '.join(map(str, self.inshape + (self.nb_feats,)))))
+        if tuple(trf.shape[1:]) != self.trf_shape + (3,):
+            raise ValueError('Transform: transform input has shape %s, expected [B, %s]'
+                             % (tuple(trf.shape), ', '.join(map(str, self.trf_shape + (3,)))))
+
+    def forward(self, inputs):
+        scan = _host.to_device(inputs[0], torch.float32, tag='scan')
+        trf = _host.to_device(inputs[1], torch.float32, tag='trf')
+        self._check(scan, trf)
+        if self.rescaler is not None:
+            trf = self.rescaler(trf)
+        return self.transformer([scan, trf])
+
+    @torch.no_grad()
+    def predict(self, inputs, copy=True, **kwargs):
+        return _host.to_host(self.forward(inputs), copy=copy)
+
+
+class VxmDense(torch.nn.Module):
+    """Deformation tail of vxm.networks.VxmDense: given the flow the
+    U-Net's flow convolution emits, ``RescaleTransform`` to the SVF / integration resolution,
+    ``VecInt(int_steps)``, ``RescaleTransform`` back to full resolution and the linear
+    ``SpatialTransformer`` on the source (3d_reg.py:305,310, bids_*.py:311-322,
+    train_synthmorph.py:296-297).
+
+    The U-Net itself (dense convolutions) is outside the hot path: pass ``flow_model``, a
+    callable ``(source, target) -> flow``, to get the full ``[source, target]`` call; without
+    it, call ``deform([source, flow])``.  Outputs ``[y_source, preint_flow]`` like the
+    reference default (``reg_field='preintegrated'``); ``references.pos_flow`` holds the
+    full-resolution integrated warp of the last call (train_synthmorph.py:297).
+    """
+
+    def __init__(self, inshape, nb_unet_features=None, int_steps=7, svf_resolution=1,
+                 int_resolution=2, fill_value=None, reg_field='preintegrated', flow_model=None,
+                 **kwargs):
+        super().__init__()
+        self.inshape = tuple(int(d) for d in inshape)
+        if len(self.inshape) != 3:
+            raise NotImplementedError('VxmDense: only 3-D volumes are supported')
+        if reg_field not in ('svf', 'preintegrated', 'postintegrated', 'warp'):
+            raise ValueError('Unknown option "%s" for reg_field.' % reg_field)
+        self.int_steps = int_steps
+        self.svf_resolution = svf_resolution
+        self.int_resolution = int_resolution
+        self.reg_field = reg_field
+        self.flow_model = flow_model
+        self.svf_size = tuple(int(np.round(d / svf_resolution)) for d in self.inshape)
+        self.int_size = tuple(int(np.round(d / int_resolution)) for d in self.inshape)
+        self.integrator = layers.VecInt(method='ss', int_steps=int_steps) if int_steps > 0 else None
+        self.transformer = layers.SpatialTransformer(interp_method='linear', indexing='ij', fill_value=fill_value)
+        self.references = types.SimpleNamespace(pos_flow=None, svf=None, preint_flow=None)
+
+    def deform(self, inputs):
+        source = _host.to_device(inputs[0], torch.float32, tag='source')
+        flow = _host.to_device(inputs[1], torch.float32, tag='flow')
+        pre_svf_size = tuple(flow.shape[1:-1])
+        svf_size = self.svf_size
+        if pre_svf_size != svf_size:
+            flow = ops.rescale_dense_transform(flow, svf_size[0] / pre_svf_size[0])
+        svf = flow
+        if self.int_steps > 0 and self.int_resolution > 1 and svf_size != self.int_size:
+            flow = ops.rescale_dense_transform(flow, self.int_size[0] / svf_size[0])
+        preint_flow = flow
+        pos_flow = flow
+        if self.int_steps > 0:
+            pos_flow = self.integrator(pos_flow)
+            if self.int_resolution > 1:
+                pos_flow = ops.rescale_dense_transform(pos_flow, self.inshape[0] / self.int_size[0])
+        y_source = self.transformer([source, pos_flow])
+        self.references.pos_flow, self.references.svf, self.references.preint_flow = pos_flow, svf, preint_flow
+        second = {'svf': svf, 'preintegrated': preint_flow}.get(self.reg_field, pos_flow)
+        return [y_source, second]
+
+    def forward(self, inputs):
+        if self.flow_model is None:
+            raise NotImplementedError(
+                'VxmDense: the U-Net is outside the B200 hot path; construct with flow_model=<callable '
+                '(source, target) -> flow> or call deform([source, flow]) with the flow it would emit')
+        source = _host.to_device(inputs[0], torch.float32, tag='source')
+        target = _host.to_device(inputs[1], torch.float32, tag='target')
+        return self.deform([source, self.flow_model(source, target)])
+
+    @torch.no_grad()
+    def predict(self, inputs, copy=True, **kwargs):
+        return [_host.to_host(t, tag='out%d' % i, copy=copy) for i, t in enumerate(self.forward(inputs))]
+
+    @torch.no_grad()
+    def predict_deform(self, inputs, copy=True):
+        """Keras-style (numpy in / numpy out) call of the deformation tail."""
+        return [_host.to_host(t, tag='out%d' % i, copy=copy) for i, t in enumerate(self.deform(inputs))]

@@ -1,0 +1,363 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): nearest-neighbour warps bit-exact; trilinear warps and
+integrated fields within 1e-5 relative / 1e-4 voxel absolute; Jacobian determinants within
+1e-4.  The forward kernels keep the oracle's op order with separately rounded fp32 ops, so the
+linear paths are in fact checked for BIT-EXACT equality; gradients (atomics, FMA) use
+tolerances.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_registration_b200 as mrb
+from multimodal_registration_b200 import ops
+from oracle import interp_oracle as io
+from oracle import jacobian_oracle as jo
+from oracle import torch_oracle as to
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-4          # north_star tolerance for fp32 linear paths
+vxm, ne = mrb.voxelmorph, mrb.neurite
+
+
+def dev(a, layout='cl'):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return ops.to_layout(t, layout) if t.dim() >= 3 else t
+
+
+def host(t):
+    return ops.to_layout(t, 'cl').cpu().numpy() if t.dim() >= 3 else t.cpu().numpy()
+
+
+def smooth_noise(rng, shape, std, smooth=2):
+    f = rng.standard_normal(shape)
+    for _ in range(smooth):
+        for ax in range(3):
+            f = (np.roll(f, 1, ax + (f.ndim - 4)) + f + np.roll(f, -1, ax + (f.ndim - 4))) / 3.0
+    return (f / f.std() * std).astype(np.float32)
+
+
+def assert_linear_parity(got, want):
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    np.testing.assert_array_equal(got, want)      # stronger: same op order -> same bits
+
+
+# --------------------------------------------------------------------------------------
+# SpatialTransformer forward
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(8, 12, 16), (7, 9, 11), (16, 16, 24)])
+@pytest.mark.parametrize('C', [1, 3])
+@pytest.mark.parametrize('std', [0.5, 4.0])
+@pytest.mark.parametrize('img_layout,field_layout', [('cl', 'cl'), ('planar', 'planar'), ('cl', 'planar')])
+def test_warp_linear(shape, C, std, img_layout, field_layout):
+    rng = np.random.default_rng(hash((shape, C, std)) % 2 ** 32)
+    B = 2
+    img = rng.random((B,) + shape + (C,)).astype(np.float32)
+    field = smooth_noise(rng, (B,) + shape + (3,), std)
+    want = io.spatial_transformer(img, field, 'linear')
+    got = host(ops.warp(dev(img, img_layout), dev(field, field_layout), 'linear'))
+    assert_linear_parity(got, want)
+
+
+@pytest.mark.parametrize('shape', [(8, 12, 16), (7, 9, 11)])
+@pytest.mark.parametrize('dtype', [np.float32, np.uint8, np.int16, np.int32, np.float64])
+@pytest.mark.parametrize('fill', [None, 0])
+def test_warp_nearest_bit_exact(shape, dtype, fill):
+    rng = np.random.default_rng(11)
+    B, C = 2, 2
+    img = (rng.random((B,) + shape + (C,)) * 26).astype(dtype)
+    field = smooth_noise(rng, (B,) + shape + (3,), 3.0)
+    field[0, 0, 0, :4] = [[0.5, 0.5, 0.5], [1.5, -0.5, 2.5], [-3, -3, -3], [50, 50, 50]]   # ties, OOB
+    want = io.spatial_transformer(img, field, 'nearest', fill_value=fill)
+    for lay in ('cl', 'planar'):
+        got = host(ops.warp(dev(img, lay), dev(field, lay), 'nearest', fill_value=fill))
+        assert got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want)
+
+
+def test_warp_fill_value_linear_and_mismatched_grid():
+    rng = np.random.default_rng(5)
+    img = rng.random((1, 10, 12, 8, 2)).astype(np.float32)
+    field = smooth_noise(rng, (1, 6, 5, 12, 3), 5.0)       # output grid differs from the image grid
+    for fv in (None, -2.5):
+        want = io.spatial_transformer(img, field, 'linear', fill_value=fv)
+        got = host(ops.warp(dev(img), dev(field), 'linear', fill_value=fv))
+        assert got.shape == (1, 6, 5, 12, 2)
+        assert_linear_parity(got, want)
+
+
+def test_identity_and_translation_known_answers():
+    rng = np.random.default_rng(3)
+    img = rng.random((1, 8, 8, 8, 1)).astype(np.float32)
+    zero = np.zeros((1, 8, 8, 8, 3), np.float32)
+    np.testing.assert_array_equal(host(ops.warp(dev(img), dev(zero))), img)
+    s = zero.copy()
+    s[..., 1] = 3
+    got = host(ops.warp(dev(img), dev(s)))
+    np.testing.assert_array_equal(got, img[:, :, np.clip(np.arange(8) + 3, 0, 7)])
+
+
+def test_transform_channelwise():
+    rng = np.random.default_rng(9)
+    X, Y, Z, C = 6, 8, 12, 4
+    vol = rng.random((X, Y, Z, C)).astype(np.float32)
+    shift = smooth_noise(rng, (X, Y, Z, C, 3), 2.0, smooth=0)
+    want = io.transform(vol, shift)
+    got = vxm.utils.transform(vol, shift)
+    assert tuple(got.shape) == (X, Y, Z, C)
+    np.testing.assert_array_equal(host(got[None])[0], want)
+
+
+def test_interpn_absolute_locations():
+    rng = np.random.default_rng(13)
+    vol = rng.random((6, 7, 8, 2)).astype(np.float32)
+    loc = (rng.random((5, 4, 3)) * 9 - 1).astype(np.float32)
+    for method in ('linear', 'nearest'):
+        want = io.interpn(vol, loc, method)
+        got = ne.utils.interpn(vol, loc, method).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+    want = io.interpn(vol[..., 0], [loc[..., d] for d in range(3)], 'linear', fill_value=0.25)
+    got = ne.utils.interpn(vol[..., 0], [loc[..., d] for d in range(3)], 'linear', fill_value=0.25).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+# --------------------------------------------------------------------------------------
+# VecInt / compose / rescale
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(8, 8, 12), (9, 7, 10), (20, 20, 24)])
+@pytest.mark.parametrize('nsteps', [0, 1, 2, 5, 7])
+@pytest.mark.parametrize('layout', ['cl', 'planar'])
+def test_vecint(shape, nsteps, layout):
+    rng = np.random.default_rng(hash((shape, nsteps)) % 2 ** 32)
+    svf = smooth_noise(rng, (2,) + shape + (3,), 3.0)
+    want = io.vec_int(svf, nsteps)
+    for out_layout in ('planar', 'cl'):
+        got = host(ops.vecint(dev(svf, layout), nsteps, out_layout=out_layout))
+        assert_linear_parity(got, want)
+
+
+def test_vecint_constant_svf_known_answer():
+    c = np.broadcast_to(np.array([1.5, -0.75, 0.25], np.float32), (1, 8, 8, 8, 3)).copy()
+    np.testing.assert_array_equal(host(ops.vecint(dev(c), 7)), c)
+
+
+def test_vecint_layer_and_integrate_vec():
+    rng = np.random.default_rng(17)
+    svf = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0)
+    want = io.vec_int(svf, 5)
+    np.testing.assert_array_equal(host(vxm.layers.VecInt(int_steps=5)(svf)), want)
+    got = vxm.utils.integrate_vec(svf[0], nb_steps=5)
+    np.testing.assert_array_equal(host(got[None])[0], want[0])
+
+
+@pytest.mark.parametrize('layout', ['cl', 'planar'])
+def test_compose(layout):
+    rng = np.random.default_rng(19)
+    a = smooth_noise(rng, (2, 8, 12, 16, 3), 3.0)
+    b = smooth_noise(rng, (2, 8, 12, 16, 3), 1.0)
+    c = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0)
+    want = np.stack([io.compose([a[i], b[i]]) for i in range(2)])
+    assert_linear_parity(host(ops.compose([dev(a, layout), dev(b, layout)])), want)
+    want3 = np.stack([io.compose([a[i], b[i], c[i]]) for i in range(2)])
+    assert_linear_parity(host(ops.compose([dev(a, layout), dev(b, layout), dev(c, layout)], out_layout='cl')), want3)
+    wantn = np.stack([io.compose([a[i], b[i]], 'nearest') for i in range(2)])
+    np.testing.assert_array_equal(host(ops.compose([dev(a, layout), dev(b, layout)], 'nearest')), wantn)
+    # the unbatched reference call (bids_two_steps_registration.py:324) + K.eval analogue
+    got = vxm.utils.to_numpy(vxm.utils.compose([a[0], b[0]]))
+    np.testing.assert_array_equal(got, want[0])
+    z = np.zeros_like(a)
+    np.testing.assert_array_equal(host(ops.compose([dev(a), dev(z)])), a)
+
+
+@pytest.mark.parametrize('shape,factor', [((8, 8, 12), 2), ((8, 12, 16), 0.5), ((6, 6, 8), 1), ((5, 7, 6), 2),
+                                          ((8, 8, 8), 1.5), ((10, 10, 10), 0.3)])
+@pytest.mark.parametrize('layout', ['cl', 'planar'])
+def test_rescale_dense_transform(shape, factor, layout):
+    rng = np.random.default_rng(23)
+    f = smooth_noise(rng, (2,) + shape + (3,), 2.0, smooth=1)
+    want = io.rescale_dense_transform(f, factor)
+    for out_layout in ('planar', 'cl'):
+        got = host(ops.rescale_dense_transform(dev(f, layout), factor, out_layout=out_layout))
+        assert got.shape == want.shape
+        assert_linear_parity(got, want)
+    wantn = io.rescale_dense_transform(f, factor, 'nearest')
+    np.testing.assert_array_equal(host(ops.rescale_dense_transform(dev(f, layout), factor, 'nearest')), wantn)
+    # unbatched + batched dispatch of the reference function (3d_reg.py:394)
+    np.testing.assert_array_equal(host(vxm.utils.rescale_dense_transform(f, factor)), want)
+    np.testing.assert_array_equal(host(vxm.utils.rescale_dense_transform(f[0], factor)[None])[0], want[0])
+
+
+def test_resize_any_channels():
+    rng = np.random.default_rng(29)
+    vol = rng.random((6, 8, 8, 5)).astype(np.float32)
+    want = io.resize(vol, [2, 1.5, 0.5])
+    got = host(ne.utils.resize(vol, [2, 1.5, 0.5])[None])[0]
+    np.testing.assert_array_equal(got, want)
+
+
+def test_transform_model_and_vxmdense_tail():
+    rng = np.random.default_rng(31)
+    scan = rng.random((2, 8, 12, 16, 1)).astype(np.float32)
+    half = smooth_noise(rng, (2, 4, 6, 8, 3), 1.5, smooth=1)
+    for interp in ('linear', 'nearest'):
+        want = io.transform_model(scan, half, interp, rescale=2)
+        got = vxm.networks.Transform((8, 12, 16), interp_method=interp, rescale=2).predict([scan, half])
+        np.testing.assert_array_equal(got, want)
+    full = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0)
+    want = io.transform_model(scan, full, 'linear', rescale=1)       # 3d_reg.py:317,333: scale == 1
+    got = vxm.networks.Transform((8, 12, 16), rescale=1).predict([scan, full])
+    np.testing.assert_array_equal(got, want)
+    # VxmDense tail: svf at half res -> VecInt(5) -> x2 -> linear warp; second output = preint flow
+    model = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2)
+    y, pre = model.predict_deform([scan, half])
+    flow = io.rescale_dense_transform(io.vec_int(half, 5), 2)
+    np.testing.assert_array_equal(y, io.spatial_transformer(scan, flow))
+    np.testing.assert_array_equal(pre, half)
+    np.testing.assert_array_equal(host(model.references.pos_flow), flow)
+
+
+# --------------------------------------------------------------------------------------
+# Jacobian determinant
+# --------------------------------------------------------------------------------------
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'jacobian_*.npz')))
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_jacobian_against_reference_golden(path):
+    g = np.load(path)
+    field = g['field'][None]
+    for layout in ('cl', 'planar'):
+        for in_dtype in (np.float32, np.float64):
+            det, stats = ops.jacobian_determinant(dev(field.astype(in_dtype), layout))
+            det = det.cpu().numpy().reshape(-1)
+            np.testing.assert_allclose(det, g['det'], rtol=0, atol=1e-4)       # north_star bar
+            np.testing.assert_allclose(det, g['det'], rtol=1e-12, atol=1e-12)  # what fp64 really gives
+            n_neg, s, s2, n = stats.cpu().numpy()[0]
+            assert int(n_neg) == int(g['n_neg']) and int(n) == g['det'].size
+            assert abs(s / n - float(g['mean'])) < 1e-12
+            assert abs(np.sqrt(max(s2 / n - (s / n) ** 2, 0)) - float(g['std'])) < 1e-9
+    det32, _ = ops.jacobian_determinant(dev(field), out_dtype=torch.float32, want_stats=False)
+    np.testing.assert_allclose(det32.cpu().numpy().reshape(-1), g['det'], rtol=0, atol=1e-4)
+
+
+def test_jacobian_batched_and_oracle():
+    rng = np.random.default_rng(37)
+    f = smooth_noise(rng, (3, 12, 10, 14, 3), 1.0)
+    det, stats = ops.jacobian_determinant(dev(f, 'planar'))
+    for b in range(3):
+        d, n = jo.jacobian_determinant(f[b][:, :, :, None, :])
+        np.testing.assert_allclose(det[b].cpu().numpy().reshape(-1), d, rtol=1e-12, atol=1e-12)
+        assert int(stats[b, 0].item()) == n
+
+
+# --------------------------------------------------------------------------------------
+# backward passes (oracle = autograd of the torch restatement; fp32 kernels vs fp64 oracle)
+# --------------------------------------------------------------------------------------
+def _grads_oracle(fn, *arrs):
+    ts = [torch.from_numpy(a.astype(np.float64)).requires_grad_(True) for a in arrs]
+    out = fn(*ts)
+    g = torch.from_numpy(np.random.default_rng(1).standard_normal(tuple(out.shape))).to(out.dtype)
+    out.backward(g)
+    return g.numpy().astype(np.float32), [t.grad.numpy() for t in ts]
+
+
+@pytest.mark.parametrize('C,layout', [(1, 'cl'), (3, 'cl'), (3, 'planar')])
+@pytest.mark.parametrize('fill', [None, 0.0])
+def test_warp_backward(C, layout, fill):
+    rng = np.random.default_rng(41)
+    img = rng.random((2, 6, 8, 10, C))
+    field = smooth_noise(rng, (2, 6, 8, 10, 3), 2.5).astype(np.float64)
+    g, (gi, gf) = _grads_oracle(lambda i, f: to.spatial_transformer(i, f, 'linear', fill), img, field)
+    ti = dev(img.astype(np.float32), layout).requires_grad_(True)
+    tf_ = dev(field.astype(np.float32), layout).requires_grad_(True)
+    out = ops.warp(ti, tf_, 'linear', fill)
+    out.backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(ti.grad), gi, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(host(tf_.grad), gf, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('nsteps', [1, 3, 5])
+def test_vecint_backward(nsteps):
+    rng = np.random.default_rng(43)
+    svf = smooth_noise(rng, (2, 6, 8, 10, 3), 2.0).astype(np.float64)
+    g, (gs,) = _grads_oracle(lambda s: to.vec_int(s, nsteps), svf)
+    ts = dev(svf.astype(np.float32)).requires_grad_(True)
+    ops.vecint(ts, nsteps).backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(ts.grad), gs, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('factor', [2, 0.5, 1.5])
+def test_rescale_backward_and_adjointness(factor):
+    rng = np.random.default_rng(47)
+    f = smooth_noise(rng, (2, 6, 8, 8, 3), 1.0).astype(np.float64)
+    g, (gf,) = _grads_oracle(lambda t: to.rescale_dense_transform(t, factor), f)
+    tf_ = dev(f.astype(np.float32)).requires_grad_(True)
+    out = ops.rescale_dense_transform(tf_, factor)
+    out.backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(tf_.grad), gf, rtol=1e-4, atol=1e-5)
+    # <K x, y> == <x, K^T y>
+    lhs = float((host(out.detach()).astype(np.float64) * g).sum())
+    rhs = float((f * host(tf_.grad)).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_compose_backward():
+    rng = np.random.default_rng(53)
+    a = smooth_noise(rng, (1, 6, 8, 10, 3), 2.0).astype(np.float64)
+    b = smooth_noise(rng, (1, 6, 8, 10, 3), 1.0).astype(np.float64)
+    g, (ga, gb) = _grads_oracle(lambda x, y: to.compose([x[0], y[0]])[None], a, b)
+    ta = dev(a.astype(np.float32)).requires_grad_(True)
+    tb = dev(b.astype(np.float32)).requires_grad_(True)
+    ops.compose([ta, tb]).backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(ta.grad), ga, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(host(tb.grad), gb, rtol=1e-4, atol=2e-5)
+
+
+def test_training_tail_gradient_chain():
+    """config.json-shaped chain at toy size: svf -> VecInt(5) -> x2 -> linear warp of a C-channel
+    one-hot map, gradient w.r.t. the svf (train_synthmorph.py:296-298,305-306)."""
+    rng = np.random.default_rng(59)
+    svf = smooth_noise(rng, (1, 4, 6, 8, 3), 1.0).astype(np.float64)
+    lab = rng.integers(0, 4, (1, 8, 12, 16))
+    onehot = np.eye(4)[lab]
+    g, (gs,) = _grads_oracle(
+        lambda s: to.spatial_transformer(torch.from_numpy(onehot), to.rescale_dense_transform(to.vec_int(s, 5), 2)), svf)
+    ts = dev(svf.astype(np.float32)).requires_grad_(True)
+    model = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2)
+    model.deform([np.zeros((1, 8, 12, 16, 1), np.float32), ts])
+    pred = vxm.layers.SpatialTransformer(interp_method='linear', name='pred')([dev(onehot.astype(np.float32)), model.references.pos_flow])
+    pred.backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(ts.grad), gs, rtol=5e-4, atol=5e-5)
+
+
+# --------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE shapes)
+# --------------------------------------------------------------------------------------
+def test_full_size_properties():
+    torch.manual_seed(0)
+    B, X, Y, Z = 2, 80, 80, 96
+    # constant SVF integrates to itself; x2 rescale of a constant doubles it; identity warp
+    c = torch.tensor([1.25, -0.5, 2.0], device='cuda').expand(B, X, Y, Z, 3).contiguous()
+    flow = ops.vecint(c, 7)
+    assert torch.equal(ops.to_layout(flow, 'cl'), c)
+    up = ops.rescale_dense_transform(flow, 2)
+    assert tuple(up.shape) == (B, 160, 160, 192, 3)
+    assert torch.allclose(ops.to_layout(up, 'cl'), 2 * c[:, :1, :1, :1].expand(B, 160, 160, 192, 3), rtol=1e-6, atol=0)
+    img = torch.rand(B, 160, 160, 192, 1, device='cuda')
+    zero = torch.zeros(B, 160, 160, 192, 3, device='cuda')
+    assert torch.equal(ops.warp(img, zero), img)
+    assert torch.equal(ops.warp(img, zero, 'nearest'), img)
+    # layouts agree bit for bit on a random smooth field at full size
+    svf = torch.nn.functional.interpolate(torch.randn(B, 3, 10, 10, 12, device='cuda') * 3, size=(X, Y, Z),
+                                          mode='trilinear').permute(0, 2, 3, 4, 1).contiguous()
+    a = ops.to_layout(ops.vecint(svf, 7), 'cl')
+    b = ops.vecint(ops.to_layout(svf, 'planar'), 7, out_layout='cl')
+    assert torch.equal(a, b)
+    # Jacobian of the zero field is 1, of an affine field det(I + A)
+    det, stats = ops.jacobian_determinant(torch.zeros(1, 64, 64, 64, 3, device='cuda'))
+    assert torch.all(det == 1) and stats[0, 0].item() == 0 and stats[0, 3].item() == 60 ** 3
