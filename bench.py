@@ -230,15 +230,15 @@ def run_own(args):
         stage_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / args.steps for i in range(3)]
 
         # ---- e2e: numpy-in / numpy-out through the Keras-style call, pinned host buffers ----
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
+        e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+        for _ in range(0 if args.no_e2e else 2):
             model.predict_deform([img_pin, svf_pin], copy=False)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             moved, _pre = model.predict_deform([img_pin, svf_pin], copy=False)
         barrier()
-        e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / max(e2e_steps, 1)
         clocks = sampler.stop() if rank == 0 else None
 
     ms = torch.tensor([total_ms / args.steps, e2e_ms] + stage_ms, device=dev, dtype=torch.float64)
@@ -265,7 +265,7 @@ def run_own(args):
         dom = kernels[dom_name]
         cores = os.cpu_count() or 1
         n_cpu = 2
-        cpu_s = cpu_pipeline_seconds(n_cpu)
+        cpu_s = float('nan') if args.no_e2e else cpu_pipeline_seconds(n_cpu)
         line = {
             'metric': METRIC, 'value': voxels / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
@@ -304,6 +304,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=32, help='volume pairs per GPU per step')
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--no-e2e', action='store_true', help='skip the e2e and cpu_baseline legs (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
