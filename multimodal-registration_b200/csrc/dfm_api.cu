@@ -28,3 +28,4 @@ int check_launch(const char *what) {
 
 extern "C" int dfm_version(void) { return DFM_VERSION; }
 extern "C" const char *dfm_last_error(void) { return dfm::err_buf(); }
+

@@ -25,6 +25,14 @@ int check_launch(const char *what);
 int scale_copy_to_planar(const float *in, float *out, int B, size_t N, float scale, bool in_cl,
                          cudaStream_t st);
 
+int validate_grid(const char *who, int B, int X, int Y, int Z);
+
+// TMA-brick path of out = scale*own + interp(scale*src, p + scale*own) -- dfm_brick.cu
+bool brick_eligible(const float *src, const float *own, const float *out, int Xs, int Ys, int Zs, int X,
+                    int Y, int Z, unsigned flags);
+int launch_ss_brick(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
+                    int Y, int Z, float scale, int large_box, cudaStream_t st);
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // n / d for n*d < 2^32 via one umulhi (host checks the range)

@@ -1,107 +1,223 @@
 // ne.utils.resize / rescale_dense_transform: resample C channels onto a separable coordinate
 // grid given by per-axis tables (tf.linspace(0, n_in-1, n_out) in the reference).
 //   out[b,c,jx,jy,jz] = post * interp(pre * in[b,c], (cx[jx], cy[jy], cz[jz]))
-// The x/y axis set-up is uniform along an output row, so a thread computes it once for its
-// VEC consecutive z outputs; the input (1/8 of the output for a x2 upsample) stays in L1/L2.
+// Direct kernel: lanes own consecutive z outputs, a thread owns ROWS consecutive rows; the
+// input (1/8 of the output for a x2 upsample) stays in L1/L2.
 #include "dfm_common.cuh"
 
 namespace dfm {
 
-template <int VEC, int INTERP, bool IN_CL, bool OUT_CL>
+template <int ROWS, int INTERP, bool IN_CL, bool OUT_CL>
 __global__ void __launch_bounds__(256)
 k_resize(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ cx,
          const float *__restrict__ cy, const float *__restrict__ cz, int C, int Xi, int Yi, int Zi,
-         int Xo, int Yo, int Zo, float pre, float post, FastDiv zvdiv, uint32_t plane_items) {
+         int Xo, int Yo, int Zo, float pre, float post, FastDiv zdiv, uint32_t plane_items) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plane_items) return;
-    const uint32_t jy = fast_div(p, zvdiv);
-    const uint32_t jz = (p - jy * zvdiv.d) * VEC;
+    const uint32_t yy = fast_div(p, zdiv);
+    const uint32_t jz = p - yy * zdiv.d;
     const uint32_t jx = blockIdx.y;
-    const size_t No = (size_t)Xo * Yo * Zo, Ni = (size_t)Xi * Yi * Zi;
-    const size_t vox = ((size_t)jx * Yo + jy) * Zo + jz;
+    const uint32_t No = (uint32_t)Xo * Yo * Zo, Ni = (uint32_t)Xi * Yi * Zi;
     const float *ib = in + (size_t)blockIdx.z * C * Ni;
     float *ob = out + (size_t)blockIdx.z * C * No;
-    const float lx = __ldg(cx + jx), ly = __ldg(cy + jy);
+    const float lx = __ldg(cx + jx), lz = __ldg(cz + jz);
+    const uint32_t YZ = (uint32_t)Yi * Zi;
 
     if (INTERP == DFM_LINEAR) {
         const Axis ax = axis_linear(lx, (float)(Xi - 1));
-        const Axis ay = axis_linear(ly, (float)(Yi - 1));
-        const uint32_t YZ = (uint32_t)Yi * Zi;
-        const uint32_t b00 = ax.i0 * YZ + ay.i0 * Zi, b01 = ax.i0 * YZ + ay.i1 * Zi;
-        const uint32_t b10 = ax.i1 * YZ + ay.i0 * Zi, b11 = ax.i1 * YZ + ay.i1 * Zi;
-        const float w00 = __fmul_rn(ax.w0, ay.w0), w01 = __fmul_rn(ax.w0, ay.w1);
-        const float w10 = __fmul_rn(ax.w1, ay.w0), w11 = __fmul_rn(ax.w1, ay.w1);
-        uint32_t off[VEC][8];
-        float w[VEC][8];
+        const Axis az = axis_linear(lz, (float)(Zi - 1));
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const Axis az = axis_linear(__ldg(cz + jz + i), (float)(Zi - 1));
-            off[i][0] = b00 + az.i0; off[i][1] = b00 + az.i1; off[i][2] = b01 + az.i0; off[i][3] = b01 + az.i1;
-            off[i][4] = b10 + az.i0; off[i][5] = b10 + az.i1; off[i][6] = b11 + az.i0; off[i][7] = b11 + az.i1;
-            w[i][0] = __fmul_rn(w00, az.w0); w[i][1] = __fmul_rn(w00, az.w1);
-            w[i][2] = __fmul_rn(w01, az.w0); w[i][3] = __fmul_rn(w01, az.w1);
-            w[i][4] = __fmul_rn(w10, az.w0); w[i][5] = __fmul_rn(w10, az.w1);
-            w[i][6] = __fmul_rn(w11, az.w0); w[i][7] = __fmul_rn(w11, az.w1);
-        }
-        for (int c = 0; c < C; ++c) {
-            float r[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t jy = yy * ROWS + r;
+            if (jy >= (uint32_t)Yo) break;
+            const Axis ay = axis_linear(__ldg(cy + jy), (float)(Yi - 1));
+            const uint32_t b00 = ax.i0 * YZ + ay.i0 * Zi, b01 = ax.i0 * YZ + ay.i1 * Zi;
+            const uint32_t b10 = ax.i1 * YZ + ay.i0 * Zi, b11 = ax.i1 * YZ + ay.i1 * Zi;
+            const float w00 = __fmul_rn(ax.w0, ay.w0), w01 = __fmul_rn(ax.w0, ay.w1);
+            const float w10 = __fmul_rn(ax.w1, ay.w0), w11 = __fmul_rn(ax.w1, ay.w1);
+            uint32_t off[8];
+            float w[8];
+            off[0] = b00 + az.i0; off[1] = b00 + az.i1; off[2] = b01 + az.i0; off[3] = b01 + az.i1;
+            off[4] = b10 + az.i0; off[5] = b10 + az.i1; off[6] = b11 + az.i0; off[7] = b11 + az.i1;
+            w[0] = __fmul_rn(w00, az.w0); w[1] = __fmul_rn(w00, az.w1);
+            w[2] = __fmul_rn(w01, az.w0); w[3] = __fmul_rn(w01, az.w1);
+            w[4] = __fmul_rn(w10, az.w0); w[5] = __fmul_rn(w10, az.w1);
+            w[6] = __fmul_rn(w11, az.w0); w[7] = __fmul_rn(w11, az.w1);
+            const uint32_t vox = (jx * Yo + jy) * Zo + jz;
+            const float *ic = ib;
+            float *oc = OUT_CL ? ob + (size_t)vox * C : ob + vox;
+            for (int c = 0; c < C; ++c) {
                 float val[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float t = IN_CL ? __ldg(ib + (size_t)off[i][k] * C + c) : __ldg(ib + (size_t)c * Ni + off[i][k]);
-                    val[k] = __fmul_rn(pre, t);
-                }
-                r[i] = __fmul_rn(post, tri_accumulate(w[i], val));
-            }
-            if (OUT_CL) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) ob[(vox + i) * C + c] = r[i];
-            } else if (VEC == 4) {
-                *reinterpret_cast<float4 *>(ob + (size_t)c * No + vox) = make_float4(r[0], r[1], r[2], r[3]);
-            } else {
-                ob[(size_t)c * No + vox] = r[0];
+                for (int k = 0; k < 8; ++k)
+                    val[k] = __fmul_rn(pre, IN_CL ? __ldg(ic + (size_t)off[k] * C) : __ldg(ic + off[k]));
+                *oc = __fmul_rn(post, tri_accumulate(w, val));
+                ic += IN_CL ? 1 : Ni;
+                oc += OUT_CL ? 1 : No;
             }
         }
     } else {
-        const uint32_t bxy = ((uint32_t)axis_nearest(lx, Xi - 1) * Yi + axis_nearest(ly, Yi - 1)) * Zi;
-        uint32_t off[VEC];
+        const uint32_t bxz = (uint32_t)axis_nearest(lx, Xi - 1) * YZ + axis_nearest(lz, Zi - 1);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) off[i] = bxy + axis_nearest(__ldg(cz + jz + i), Zi - 1);
-        for (int c = 0; c < C; ++c) {
-            float r[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float t = IN_CL ? __ldg(ib + (size_t)off[i] * C + c) : __ldg(ib + (size_t)c * Ni + off[i]);
-                r[i] = __fmul_rn(post, __fmul_rn(pre, t));
-            }
-            if (OUT_CL) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) ob[(vox + i) * C + c] = r[i];
-            } else if (VEC == 4) {
-                *reinterpret_cast<float4 *>(ob + (size_t)c * No + vox) = make_float4(r[0], r[1], r[2], r[3]);
-            } else {
-                ob[(size_t)c * No + vox] = r[0];
+        for (int r = 0; r < ROWS; ++r) {
+            const uint32_t jy = yy * ROWS + r;
+            if (jy >= (uint32_t)Yo) break;
+            const uint32_t off = bxz + (uint32_t)axis_nearest(__ldg(cy + jy), Yi - 1) * Zi;
+            const uint32_t vox = (jx * Yo + jy) * Zo + jz;
+            const float *ic = IN_CL ? ib + (size_t)off * C : ib + off;
+            float *oc = OUT_CL ? ob + (size_t)vox * C : ob + vox;
+            for (int c = 0; c < C; ++c) {
+                *oc = __fmul_rn(post, __fmul_rn(pre, __ldg(ic)));
+                ic += IN_CL ? 1 : Ni;
+                oc += OUT_CL ? 1 : No;
             }
         }
     }
 }
 
-template <int VEC, int INTERP>
+template <int INTERP>
 static int launch_resize(const float *in, float *out, const float *cx, const float *cy, const float *cz, int B,
                          int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo, float pre, float post,
                          unsigned flags, cudaStream_t st) {
-    const uint32_t zv = Zo / VEC, plane = (uint32_t)Yo * zv;
+    constexpr int ROWS = 4;
+    const uint32_t plane = (uint32_t)((Yo + ROWS - 1) / ROWS) * Zo;
     dim3 grid((plane + 255) / 256, Xo, B), block(256);
-    FastDiv fd = make_fastdiv(zv);
+    FastDiv fd = make_fastdiv(Zo);
     const bool icl = flags & DFM_FIELD_IN_CL, ocl = flags & DFM_FIELD_OUT_CL;
-#define DFM_GO(I, O) k_resize<VEC, INTERP, I, O><<<grid, block, 0, st>>>( \
+#define DFM_GO(I, O) k_resize<ROWS, INTERP, I, O><<<grid, block, 0, st>>>( \
         in, out, cx, cy, cz, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, fd, plane)
     if (icl) { if (ocl) DFM_GO(true, true); else DFM_GO(true, false); }
     else     { if (ocl) DFM_GO(false, true); else DFM_GO(false, false); }
 #undef DFM_GO
     return check_launch("dfm_resize_fwd");
+}
+
+// ---------------------------------------------------------------------------------------
+// Up-sampling of a planar 3-component field through shared memory (the x2 RescaleTransform of
+// VxmDense).  A CTA owns 8 x 8 x 64 outputs; the input box they sample (about 6 x 6 x 34 for
+// x2) is staged once as float4 {c0, c1, c2, -} so that one 128-bit shared load fetches all
+// three components of a corner: 8 LDS.128 per output voxel instead of 24 LDS.32, and because
+// neighbouring outputs share input voxels (pairs of lanes hit the same address -> broadcast)
+// the crossbar moves half as many wavefronts.  Same op order as the direct kernel.  If the
+// box does not fit the allocation (general tables), the CTA gathers from global memory.
+// ---------------------------------------------------------------------------------------
+constexpr int RT_X = 8, RT_Y = 8, RT_Z = 64;
+
+__device__ __forceinline__ int axis_i0(float loc, int maxi) {
+    return (int)fminf(fmaxf(floorf(loc), 0.f), (float)maxi);
+}
+
+__global__ void __launch_bounds__(256)
+k_resize3_smem(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ cx,
+               const float *__restrict__ cy, const float *__restrict__ cz, int Xi, int Yi, int Zi, int Xo,
+               int Yo, int Zo, float pre, float post, int nzt, int cap_x, int cap_y, int cap_z) {
+    extern __shared__ float4 box[];                       // [nbx][nby][nbz]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
+    const int jx0 = blockIdx.y * RT_X, jy0 = yt * RT_Y, jz0 = zt * RT_Z;
+    const int jx1 = min(jx0 + RT_X, Xo) - 1, jy1 = min(jy0 + RT_Y, Yo) - 1, jz1 = min(jz0 + RT_Z, Zo) - 1;
+    const uint32_t No = (uint32_t)Xo * Yo * Zo, Ni = (uint32_t)Xi * Yi * Zi;
+    const float *ib = in + (size_t)blockIdx.z * 3 * Ni;
+    float *ob = out + (size_t)blockIdx.z * 3 * No;
+    // input box of this tile (tables are non-decreasing): [i0(first), min(i0(last) + 1, max)]
+    const int bx0 = axis_i0(__ldg(cx + jx0), Xi - 1), bx1 = min(axis_i0(__ldg(cx + jx1), Xi - 1) + 1, Xi - 1);
+    const int by0 = axis_i0(__ldg(cy + jy0), Yi - 1), by1 = min(axis_i0(__ldg(cy + jy1), Yi - 1) + 1, Yi - 1);
+    const int bz0 = axis_i0(__ldg(cz + jz0), Zi - 1), bz1 = min(axis_i0(__ldg(cz + jz1), Zi - 1) + 1, Zi - 1);
+    const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1, nbz = bz1 - bz0 + 1;
+    const bool staged = nbx <= cap_x && nby <= cap_y && nbz <= cap_z;     // CTA-uniform
+    if (staged) {
+        const int total = nbx * nby * nbz;
+        for (int t = threadIdx.x; t < total; t += 256) {
+            const int bz = t % nbz, q = t / nbz, by = q % nby, bx = q / nby;
+            const uint32_t o = ((uint32_t)(bx0 + bx) * Yi + (by0 + by)) * Zi + (bz0 + bz);
+            box[t] = make_float4(__fmul_rn(pre, __ldg(ib + o)), __fmul_rn(pre, __ldg(ib + Ni + o)),
+                                 __fmul_rn(pre, __ldg(ib + 2 * (size_t)Ni + o)), 0.f);
+        }
+    }
+    __syncthreads();
+
+    const int jy = jy0 + warp;
+    if (jy >= Yo) return;
+    const Axis ay = axis_linear(__ldg(cy + jy), (float)(Yi - 1));
+    Axis az[2];
+    bool okz[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int jz = jz0 + s * 32 + lane;
+        okz[s] = jz < Zo;
+        az[s] = axis_linear(__ldg(cz + min(jz, Zo - 1)), (float)(Zi - 1));
+    }
+#pragma unroll 2
+    for (int i = 0; i < RT_X; ++i) {
+        const int jx = jx0 + i;
+        if (jx >= Xo) break;
+        const Axis ax = axis_linear(__ldg(cx + jx), (float)(Xi - 1));
+        const float w00 = __fmul_rn(ax.w0, ay.w0), w01 = __fmul_rn(ax.w0, ay.w1);
+        const float w10 = __fmul_rn(ax.w1, ay.w0), w11 = __fmul_rn(ax.w1, ay.w1);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (!okz[s]) continue;
+            float w[8];
+            w[0] = __fmul_rn(w00, az[s].w0); w[1] = __fmul_rn(w00, az[s].w1);
+            w[2] = __fmul_rn(w01, az[s].w0); w[3] = __fmul_rn(w01, az[s].w1);
+            w[4] = __fmul_rn(w10, az[s].w0); w[5] = __fmul_rn(w10, az[s].w1);
+            w[6] = __fmul_rn(w11, az[s].w0); w[7] = __fmul_rn(w11, az[s].w1);
+            float v0[8], v1[8], v2[8];
+            if (staged) {
+                const int r00 = ((ax.i0 - bx0) * nby + (ay.i0 - by0)) * nbz - bz0;
+                const int r01 = ((ax.i0 - bx0) * nby + (ay.i1 - by0)) * nbz - bz0;
+                const int r10 = ((ax.i1 - bx0) * nby + (ay.i0 - by0)) * nbz - bz0;
+                const int r11 = ((ax.i1 - bx0) * nby + (ay.i1 - by0)) * nbz - bz0;
+                const int o[8] = {r00 + az[s].i0, r00 + az[s].i1, r01 + az[s].i0, r01 + az[s].i1,
+                                  r10 + az[s].i0, r10 + az[s].i1, r11 + az[s].i0, r11 + az[s].i1};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 t = box[o[k]];
+                    v0[k] = t.x; v1[k] = t.y; v2[k] = t.z;
+                }
+            } else {
+                const uint32_t YZ = (uint32_t)Yi * Zi;
+                const uint32_t b00 = ax.i0 * YZ + ay.i0 * Zi, b01 = ax.i0 * YZ + ay.i1 * Zi;
+                const uint32_t b10 = ax.i1 * YZ + ay.i0 * Zi, b11 = ax.i1 * YZ + ay.i1 * Zi;
+                const uint32_t o[8] = {b00 + az[s].i0, b00 + az[s].i1, b01 + az[s].i0, b01 + az[s].i1,
+                                       b10 + az[s].i0, b10 + az[s].i1, b11 + az[s].i0, b11 + az[s].i1};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v0[k] = __fmul_rn(pre, __ldg(ib + o[k]));
+                    v1[k] = __fmul_rn(pre, __ldg(ib + Ni + o[k]));
+                    v2[k] = __fmul_rn(pre, __ldg(ib + 2 * (size_t)Ni + o[k]));
+                }
+            }
+            const uint32_t vox = ((uint32_t)jx * Yo + jy) * Zo + (jz0 + s * 32 + lane);
+            ob[vox] = __fmul_rn(post, tri_accumulate(w, v0));
+            ob[No + vox] = __fmul_rn(post, tri_accumulate(w, v1));
+            ob[2 * (size_t)No + vox] = __fmul_rn(post, tri_accumulate(w, v2));
+        }
+    }
+}
+
+static int launch_resize3_smem(const float *in, float *out, const float *cx, const float *cy, const float *cz,
+                               int B, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo, float pre, float post,
+                               cudaStream_t st) {
+    // box capacity from the zoom ratio (+ slack); tiles whose box is larger gather from global
+    auto cap = [](int tile, int n_in, int n_out) {
+        const double ratio = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
+        return (int)(tile * ratio) + 3;
+    };
+    const int cap_x = cap(RT_X, Xi, Xo), cap_y = cap(RT_Y, Yi, Yo), cap_z = cap(RT_Z, Zi, Zo);
+    const size_t smem = (size_t)cap_x * cap_y * cap_z * sizeof(float4);
+    if (smem > 64 * 1024) return DFM_EUNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_resize3_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_resize3_smem smem attribute: %s", cudaGetErrorString(e));
+        configured = 64 * 1024;
+    }
+    const int nzt = (Zo + RT_Z - 1) / RT_Z, nyt = (Yo + RT_Y - 1) / RT_Y, nxt = (Xo + RT_X - 1) / RT_X;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    k_resize3_smem<<<grid, block, smem, st>>>(in, out, cx, cy, cz, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, nzt,
+                                              cap_x, cap_y, cap_z);
+    return check_launch("dfm_resize_fwd(smem)");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -156,8 +272,8 @@ extern "C" int dfm_resize_fwd(const float *in, float *out, const float *cx, cons
     DFM_REQUIRE(B >= 0 && C >= 1 && Xi >= 1 && Yi >= 1 && Zi >= 1 && Xo >= 0 && Yo >= 0 && Zo >= 0, DFM_EINVAL,
                 "dfm_resize_fwd: bad shape B=%d C=%d in=(%d,%d,%d) out=(%d,%d,%d)", B, C, Xi, Yi, Zi, Xo, Yo, Zo);
     DFM_REQUIRE(B <= 65535 && Xo <= 65535, DFM_EINVAL, "dfm_resize_fwd: B and Xo must be <= 65535");
-    DFM_REQUIRE((uint64_t)Xo * Yo * Zo < (1ull << 31) && (uint64_t)Xi * Yi * Zi < (1ull << 31), DFM_EINVAL,
-                "dfm_resize_fwd: volume too large (>= 2^31 voxels)");
+    DFM_REQUIRE((uint64_t)Xo * Yo * Zo < (1ull << 30) && (uint64_t)Xi * Yi * Zi < (1ull << 30), DFM_EINVAL,
+                "dfm_resize_fwd: volume too large (>= 2^30 voxels)");
     DFM_REQUIRE((uint64_t)Yo * Zo * (uint64_t)Zo < (1ull << 32), DFM_EINVAL, "dfm_resize_fwd: Yo*Zo*Zo must be < 2^32");
     DFM_REQUIRE(interp == DFM_LINEAR || interp == DFM_NEAREST, DFM_EINVAL, "dfm_resize_fwd: interp %d", interp);
     if (B == 0 || Xo == 0 || Yo == 0 || Zo == 0) return DFM_OK;
@@ -165,12 +281,14 @@ extern "C" int dfm_resize_fwd(const float *in, float *out, const float *cx, cons
     DFM_REQUIRE(in != out, DFM_EINVAL, "dfm_resize_fwd: out must not alias in");
     if (C == 1) flags &= ~(DFM_FIELD_IN_CL | DFM_FIELD_OUT_CL);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec4 = (Zo % 4 == 0) && aligned16(out);
-    if (interp == DFM_LINEAR)
-        return vec4 ? launch_resize<4, DFM_LINEAR>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st)
-                    : launch_resize<1, DFM_LINEAR>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
-    return vec4 ? launch_resize<4, DFM_NEAREST>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st)
-                : launch_resize<1, DFM_NEAREST>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
+    if (interp == DFM_LINEAR) {
+        if (C == 3 && !(flags & (DFM_FIELD_IN_CL | DFM_FIELD_OUT_CL)) && Xo >= Xi && Yo >= Yi && Zo >= Zi) {
+            int rc = launch_resize3_smem(in, out, cx, cy, cz, B, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, st);
+            if (rc != DFM_EUNSUPPORTED) return rc;
+        }
+        return launch_resize<DFM_LINEAR>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
+    }
+    return launch_resize<DFM_NEAREST>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
 }
 
 extern "C" int dfm_resize_bwd(const float *gout, float *gin, const float *cx, const float *cy, const float *cz,
