@@ -1,0 +1,32 @@
+"""Summarise an .ncu-rep (ncu --page raw --csv) into the handful of metrics we track."""
+import csv, subprocess, sys, io
+rep = sys.argv[1]
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'smsp__inst_executed.sum', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
+idx = [hdr.index(w) if w in hdr else None for w in want]
+out = csv.writer(sys.stdout)
+out.writerow(want)
+out.writerow([units[i] if i is not None else '' for i in idx])
+seen = set()
+for r in data:
+    name = r[idx[0]].split('(')[0]
+    if len(sys.argv) > 2 and name in seen:
+        continue
+    seen.add(name)
+    out.writerow([(r[i] if i is not None else '') for i in idx])
