@@ -52,6 +52,10 @@ extern "C" {
                                instead of displacements added to the voxel grid */
 
 int dfm_version(void);
+/* 1: this build keeps the reference's op order with separately rounded fp32 ops (libdfm_exact.so,
+ * bit-identical to the oracle); 0: fused/packed accumulation (libdfm.so, the default; differs by the
+ * removed intermediate roundings only, ~1e-7 relative). */
+int dfm_exact_order(void);
 const char *dfm_last_error(void);
 
 /* ---------------------------------------------------------------------------------------
@@ -72,6 +76,19 @@ int dfm_warp_fwd(const void *img, const float *field, void *out,
                  int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z,
                  int interp, int elem_size, int has_fill, float fill, uint64_t fill_bits,
                  unsigned flags, void *stream);
+
+/* Fused RescaleTransform(factor >= 1) + linear SpatialTransformer of a one-channel image: the
+ * deformation tail of VxmDense at inference (3d_reg.py:305,310; bids_*.py:311-322), where the
+ * full-resolution warp is only an intermediate.  out[b,p] = interp(img[b], p + U[b,:,p]) with
+ * U = resize(factor * coarse) evaluated on the fly (same arithmetic as dfm_resize_fwd followed
+ * by dfm_warp_fwd, bit for bit), so U never touches HBM.
+ *   img [B][Xi][Yi][Zi], coarse [B][3][Xh][Yh][Zh] planar, out [B][X][Y][Z]; cx/cy/cz as in
+ *   dfm_resize_fwd (X/Y/Z entries).  work: nullable scratch of B*3*X*Y*Z floats used when the
+ *   fused kernel is not applicable (then the two kernels run back to back); without it such
+ *   shapes return DFM_EUNSUPPORTED. */
+int dfm_rescale_warp_fwd(const float *img, const float *coarse, float *out, const float *cx, const float *cy,
+                         const float *cz, float *work, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh,
+                         int X, int Y, int Z, float factor, int has_fill, float fill, void *stream);
 
 /* Backward of the linear warp (TensorFlow autodiff semantics of the reference graph:
  * floor has zero gradient, clip passes gradient inside [0, max] inclusive).

@@ -6,7 +6,10 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdfm.so')
+# two builds of the same sources (csrc/Makefile): fused/packed accumulation (default) and the
+# reference's op order with separately rounded ops (bit-identical to the oracle)
+LIB_PATHS = {False: os.path.join(_HERE, 'libdfm.so'), True: os.path.join(_HERE, 'libdfm_exact.so')}
+LIB_PATH = LIB_PATHS[False]
 
 DFM_LINEAR, DFM_NEAREST = 0, 1
 FIELD_IN_CL, FIELD_OUT_CL, IMG_CL, LOC_ABSOLUTE = 1, 2, 4, 8
@@ -17,8 +20,10 @@ _p, _i, _f, _u, _z, _u64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_uint, _c.c_si
 # name -> (restype, argtypes); must list every symbol include/dfm.h declares
 SIGNATURES = {
     'dfm_version': (_i, []),
+    'dfm_exact_order': (_i, []),
     'dfm_last_error': (_c.c_char_p, []),
     'dfm_warp_fwd': (_i, [_p, _p, _p] + [_i] * 8 + [_i, _i, _i, _f, _u64, _u, _p]),
+    'dfm_rescale_warp_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _f, _p]),
     'dfm_warp_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
     'dfm_field_warp_add': (_i, [_p, _p, _p] + [_i] * 7 + [_f, _i, _u, _p]),
     'dfm_vecint_workspace_bytes': (_z, [_i] * 6),
@@ -38,24 +43,41 @@ class DfmError(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
+_exact = os.environ.get('DFM_EXACT', '0') not in ('', '0')
+
+
+def use(exact):
+    """Select the arithmetic mode for subsequent calls: False = libdfm.so (fused/packed, default),
+    True = libdfm_exact.so (reference op order, bit-identical to the oracle).  The environment
+    variable DFM_EXACT=1 selects the exact build at import time."""
+    global _exact
+    _exact = bool(exact)
+    return load()
+
+
+def exact_order():
+    return bool(load().dfm_exact_order())
 
 
 def load():
-    """Load libdfm.so once; raise loudly if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    """Load the selected library once; raise loudly if it has not been built."""
+    lib = _libs.get(_exact)
+    if lib is not None:
+        return lib
+    path = LIB_PATHS[_exact]
+    if not os.path.exists(path):
         raise DfmError(
-            'libdfm.so not found at %s -- build it with `python __graft_entry__.py` or '
-            '`make -C multimodal-registration_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            '%s not found -- build it with `python __graft_entry__.py` or '
+            '`make -C multimodal-registration_b200/csrc`. There is no CPU fallback.' % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if bool(lib.dfm_exact_order()) != _exact:
+        raise DfmError('%s reports the wrong arithmetic mode' % path)
+    _libs[_exact] = lib
     return lib
 
 

@@ -27,5 +27,6 @@ int check_launch(const char *what) {
 }  // namespace dfm
 
 extern "C" int dfm_version(void) { return DFM_VERSION; }
+extern "C" int dfm_exact_order(void) { return DFM_EXACT_ORDER; }
 extern "C" const char *dfm_last_error(void) { return dfm::err_buf(); }
 

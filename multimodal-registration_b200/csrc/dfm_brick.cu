@@ -1,17 +1,25 @@
-// TMA-staged shared-memory bricks for the gather-heavy self-warp of a scaling-and-squaring
-// step (and compose):   out = scale*own + interp(scale*src, p + scale*own),  planar fp32.
+// TMA-staged shared-memory bricks for the gather-heavy kernels (planar fp32):
+//   k_ss_brick   : out = scale*own + interp(scale*src, p + scale*own)   (SS step, compose)
+//   k_warp_brick : out = interp(img, p + field)                         (one-channel image warp)
 //
 // A CTA owns a tile of TX x TY x TZ = 8 x 8 x 32 output voxels (warp = one y row, lane = z,
 // each thread walks the 8 x planes).  Pass 1 loads the tile's own vectors (coalesced), forms
-// the sample locations and block-reduces their integer bounding box.  One elected thread then
-// issues a single 4-D TMA box load {BZ, BY, BX, 3 components} whose ORIGIN is that bounding
-// box's corner -- so the brick follows the displacement, and its size only has to cover the
-// tile plus the local deformation, not the displacement magnitude.  Pass 2 gathers the 24
-// corner values per voxel from shared memory (32-bit addressing, one wavefront per request
-// instead of two L1 lines) with the reference's op order.  A thread whose corners fall outside
-// the brick (strong local deformation) falls back to global gathers, so the result never
-// depends on the brick size.  TMA zero-fills out-of-volume elements; they are never read
-// because corner indices are clamped to the volume first (edge clamp of the reference).
+// the sample locations and block-reduces the integer bounding box of their corner indices.
+// One elected thread then issues a single 4-D TMA box load whose ORIGIN is that bounding
+// box's corner -- the brick follows the displacement, so its size only has to cover the tile
+// plus the local deformation, not the displacement magnitude.  Pass 2 gathers the corner
+// values from shared memory: with the lower corner addressed as i1 - 1 (dfm_common.cuh) the 8
+// corners are ONE base address plus compile-time offsets, i.e. 24 LDS with immediates and ~4
+// address instructions per voxel (the direct kernel spends ~120 on 64-bit addressing).
+// The brick's z pitch is 64 floats: every row and plane starts on bank 0, so lanes whose
+// x/y corner rows differ still hit distinct banks.  Tiles whose box does not fit the brick
+// (strong local deformation) take a per-thread checked path with global-memory gathers, so
+// the result never depends on the brick size.  TMA zero-fills out-of-volume elements; they
+// are only ever multiplied by an exactly-zero weight.
+//
+// Measured on sm_100a (scripts/tma_probe.cu): the innermost TMA coordinate must be a multiple
+// of 16 bytes, otherwise the copy raises an illegal-instruction fault -> the box origin is
+// aligned down to 4 floats in z.
 #include <cuda.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -53,9 +61,40 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tmap, 
         : "memory");
 }
 
-constexpr int TX = 8, TY = 8, TZ = 32;
+constexpr int TY = 8, TZ = 32;
 
-template <int BX, int BY, int BZ>
+// block-wide bounding box of the corner indices: lower corner i1 - 1, upper corner i1
+struct BoxReduce {
+    int mn[3], mx[3];
+    __device__ __forceinline__ void init() {
+        mn[0] = mn[1] = mn[2] = INT_MAX;
+        mx[0] = mx[1] = mx[2] = INT_MIN;
+    }
+    __device__ __forceinline__ void add(int ix, int iy, int iz) {
+        mn[0] = min(mn[0], ix); mn[1] = min(mn[1], iy); mn[2] = min(mn[2], iz);
+        mx[0] = max(mx[0], ix); mx[1] = max(mx[1], iy); mx[2] = max(mx[2], iz);
+    }
+    // s_min/s_max: shared int[3] initialised to INT_MAX / INT_MIN before the preceding barrier
+    __device__ __forceinline__ void commit(int *s_min, int *s_max, int lane) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = __reduce_min_sync(0xffffffffu, mn[d]);
+            mx[d] = __reduce_max_sync(0xffffffffu, mx[d]);
+        }
+        if (lane == 0 && mn[0] != INT_MAX) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(&s_min[d], mn[d] - 1);       // lower corner index
+                atomicMax(&s_max[d], mx[d]);           // upper corner index
+            }
+        }
+    }
+};
+
+// =========================================================================================
+// field self / cross warp
+// =========================================================================================
+template <int TX, int BX, int BY, int BZ, bool SCALED>
 __global__ void __launch_bounds__(256)
 k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src,
            const float *__restrict__ own, float *__restrict__ out, int Xs, int Ys, int Zs, int X, int Y,
@@ -64,7 +103,7 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     float *brick = reinterpret_cast<float *>(smem_raw);   // [3][BX][BY][BZ]
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_min[3], s_max[3];
-    constexpr int CS = BX * BY * BZ;                      // component stride in the brick
+    constexpr int PX = BY * BZ, PY = BZ, CS = BX * BY * BZ;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
@@ -72,8 +111,12 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     const bool ok_yz = (z < Z) && (y < Y);
     const uint32_t N = (uint32_t)X * Y * Z, Ns = (uint32_t)Xs * Ys * Zs;
     const float *ownb = own + (size_t)blockIdx.z * 3 * N;
-    const float *srcb = src + (size_t)blockIdx.z * 3 * Ns;
     float *outb = out + (size_t)blockIdx.z * 3 * N;
+    const int mxi = Xs - 1, myi = Ys - 1, mzi = Zs - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float fy = (float)y, fz = (float)z, fx0 = (float)x0;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + y) * Z + z, XS = (uint32_t)Y * Z;
+    const int nx = ok_yz ? min(TX, X - x0) : 0;          // voxels this thread owns
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -82,50 +125,35 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     }
     __syncthreads();
 
-    // ---- pass 1: own vectors, sample locations, bounding box of the corner indices --------
-    const float mxf = (float)(Xs - 1), myf = (float)(Ys - 1), mzf = (float)(Zs - 1);
-    const float fy = (float)y, fz = (float)z;
+    // ---- pass 1: own vectors, sample locations, bounding box --------------------------------
     float v[3][TX];
-    int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN;
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
-        const int x = x0 + i;
-        if (ok_yz && x < X) {
-            const uint32_t vox = ((uint32_t)x * Y + y) * Z + z;
-            v[0][i] = __fmul_rn(scale, __ldg(ownb + vox));
-            v[1][i] = __fmul_rn(scale, __ldg(ownb + N + vox));
-            v[2][i] = __fmul_rn(scale, __ldg(ownb + 2 * (size_t)N + vox));
+        if (i < nx) {
+            const uint32_t vox = vox0 + i * XS;
+            v[0][i] = __ldg(ownb + vox);
+            v[1][i] = __ldg(ownb + N + vox);
+            v[2][i] = __ldg(ownb + 2 * (size_t)N + vox);
         } else {
             v[0][i] = v[1][i] = v[2][i] = 0.f;
         }
     }
+    BoxReduce box;
+    box.init();
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
-        const int x = x0 + i;
-        if (ok_yz && x < X) {
-            const float lx = __fadd_rn((float)x, v[0][i]), ly = __fadd_rn(fy, v[1][i]), lz = __fadd_rn(fz, v[2][i]);
-            const int ix = (int)fminf(fmaxf(floorf(lx), 0.f), mxf);
-            const int iy = (int)fminf(fmaxf(floorf(ly), 0.f), myf);
-            const int iz = (int)fminf(fmaxf(floorf(lz), 0.f), mzf);
-            mn0 = min(mn0, ix); mn1 = min(mn1, iy); mn2 = min(mn2, iz);
-            mx0 = max(mx0, ix); mx1 = max(mx1, iy); mx2 = max(mx2, iz);
+        if (SCALED) {
+            v[0][i] = __fmul_rn(scale, v[0][i]); v[1][i] = __fmul_rn(scale, v[1][i]); v[2][i] = __fmul_rn(scale, v[2][i]);
         }
+        if (i < nx)
+            box.add(axis_fast_i1(__fadd_rn(fx0 + (float)i, v[0][i]), mxf, mxi),
+                    axis_fast_i1(__fadd_rn(fy, v[1][i]), myf, myi), axis_fast_i1(__fadd_rn(fz, v[2][i]), mzf, mzi));
     }
-    mn0 = __reduce_min_sync(0xffffffffu, mn0); mn1 = __reduce_min_sync(0xffffffffu, mn1);
-    mn2 = __reduce_min_sync(0xffffffffu, mn2); mx0 = __reduce_max_sync(0xffffffffu, mx0);
-    mx1 = __reduce_max_sync(0xffffffffu, mx1); mx2 = __reduce_max_sync(0xffffffffu, mx2);
-    if (lane == 0 && mn0 != INT_MAX) {
-        atomicMin(&s_min[0], mn0); atomicMin(&s_min[1], mn1); atomicMin(&s_min[2], mn2);
-        atomicMax(&s_max[0], mx0); atomicMax(&s_max[1], mx1); atomicMax(&s_max[2], mx2);
-    }
+    box.commit(s_min, s_max, lane);
     __syncthreads();
-    // measured on sm_100a: the innermost TMA coordinate must be 16-byte aligned (a multiple of 4
-    // floats) or the copy raises an illegal-instruction fault -> align the box origin down in z
     const int ox = s_min[0], oy = s_min[1], oz = s_min[2] & ~3;
     if (ox == INT_MAX) return;                        // tile entirely outside the volume (uniform)
-    // the upper corner index is min(i0 + 1, max): the brick must reach one past the largest i0
-    const bool fits = (min(s_max[0] + 1, Xs - 1) - ox < BX) && (min(s_max[1] + 1, Ys - 1) - oy < BY) &&
-                      (min(s_max[2] + 1, Zs - 1) - oz < BZ);
+    const bool fits = (s_max[0] - ox < BX) && (s_max[1] - oy < BY) && (s_max[2] - oz < BZ);
 
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, 3u * CS * sizeof(float));
@@ -133,64 +161,275 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     }
     mbar_wait(&bar, 0);
 
-    // ---- pass 2: gather from the brick, reference op order --------------------------------
+    // ---- pass 2 ------------------------------------------------------------------------------
+    // lower-corner offset in the brick = i1x*PX + i1y*PY + i1z + cbase
+    const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
+    if (fits) {
+        // two voxels (x planes i, i+1) at a time: the packed FP32x2 pipe does both accumulations
 #pragma unroll
-    for (int i = 0; i < TX; ++i) {
-        const int x = x0 + i;
-        if (!(ok_yz && x < X)) continue;
-        const float v0 = v[0][i], v1 = v[1][i], v2 = v[2][i];
-        const Axis ax = axis_linear(__fadd_rn((float)x, v0), mxf);
-        const Axis ay = axis_linear(__fadd_rn(fy, v1), myf);
-        const Axis az = axis_linear(__fadd_rn(fz, v2), mzf);
-        float w[8];
-        {
-            const float w00 = __fmul_rn(ax.w0, ay.w0), w01 = __fmul_rn(ax.w0, ay.w1);
-            const float w10 = __fmul_rn(ax.w1, ay.w0), w11 = __fmul_rn(ax.w1, ay.w1);
-            w[0] = __fmul_rn(w00, az.w0); w[1] = __fmul_rn(w00, az.w1);
-            w[2] = __fmul_rn(w01, az.w0); w[3] = __fmul_rn(w01, az.w1);
-            w[4] = __fmul_rn(w10, az.w0); w[5] = __fmul_rn(w10, az.w1);
-            w[6] = __fmul_rn(w11, az.w0); w[7] = __fmul_rn(w11, az.w1);
-        }
-        float a0, a1, a2;
-        const bool inside = fits || ((ax.i1 - ox < BX) && (ay.i1 - oy < BY) && (az.i1 - oz < BZ));
-        if (inside) {
-            const int bx0 = (ax.i0 - ox) * (BY * BZ), bx1 = (ax.i1 - ox) * (BY * BZ);
-            const int by0 = (ay.i0 - oy) * BZ, by1 = (ay.i1 - oy) * BZ;
-            const int bz0 = az.i0 - oz, bz1 = az.i1 - oz;
-            const float *q00 = brick + bx0 + by0, *q01 = brick + bx0 + by1;
-            const float *q10 = brick + bx1 + by0, *q11 = brick + bx1 + by1;
-            float val[8];
+        for (int i = 0; i < TX; i += 2) {
+            if (i >= nx) break;
+            const bool hasB = i + 1 < nx;             // odd tail: voxel B duplicates voxel A
+            const float a0 = v[0][i], a1 = v[1][i], a2 = v[2][i];
+            const float b0 = hasB ? v[0][i + 1] : a0, b1 = hasB ? v[1][i + 1] : a1, b2 = hasB ? v[2][i + 1] : a2;
+            const float fxa = fx0 + (float)i, fxb = hasB ? fx0 + (float)(i + 1) : fxa;
+            const AxisF ax = axis_fast(__fadd_rn(fxa, a0), mxf, mxi), bx = axis_fast(__fadd_rn(fxb, b0), mxf, mxi);
+            const AxisF ay = axis_fast(__fadd_rn(fy, a1), myf, myi), by = axis_fast(__fadd_rn(fy, b1), myf, myi);
+            const AxisF az = axis_fast(__fadd_rn(fz, a2), mzf, mzi), bz = axis_fast(__fadd_rn(fz, b2), mzf, mzi);
+            float wA[8], wB[8];
+            tri_weights_pair(ax, ay, az, bx, by, bz, wA, wB);
+            const float *qa = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
+            const float *qb = brick + (bx.i1 * PX + by.i1 * PY + bz.i1 + cbase);
+            float ra[3], rb[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                val[0] = q00[c * CS + bz0]; val[1] = q00[c * CS + bz1];
-                val[2] = q01[c * CS + bz0]; val[3] = q01[c * CS + bz1];
-                val[4] = q10[c * CS + bz0]; val[5] = q10[c * CS + bz1];
-                val[6] = q11[c * CS + bz0]; val[7] = q11[c * CS + bz1];
-                const float a = tri_accumulate(w, val);
-                if (c == 0) a0 = a; else if (c == 1) a1 = a; else a2 = a;
+                const float va[8] = {qa[c * CS], qa[c * CS + 1], qa[c * CS + PY], qa[c * CS + PY + 1],
+                                     qa[c * CS + PX], qa[c * CS + PX + 1], qa[c * CS + PX + PY], qa[c * CS + PX + PY + 1]};
+                const float vb[8] = {qb[c * CS], qb[c * CS + 1], qb[c * CS + PY], qb[c * CS + PY + 1],
+                                     qb[c * CS + PX], qb[c * CS + PX + 1], qb[c * CS + PX + PY], qb[c * CS + PX + PY + 1]};
+                tri_accumulate_pair(wA, wB, va, vb, ra[c], rb[c]);
             }
-        } else {
-            const uint32_t YZ = (uint32_t)Ys * Zs;
-            uint32_t off[8];
-            const uint32_t b00 = ax.i0 * YZ + ay.i0 * Zs, b01 = ax.i0 * YZ + ay.i1 * Zs;
-            const uint32_t b10 = ax.i1 * YZ + ay.i0 * Zs, b11 = ax.i1 * YZ + ay.i1 * Zs;
-            off[0] = b00 + az.i0; off[1] = b00 + az.i1; off[2] = b01 + az.i0; off[3] = b01 + az.i1;
-            off[4] = b10 + az.i0; off[5] = b10 + az.i1; off[6] = b11 + az.i0; off[7] = b11 + az.i1;
-            float val[8];
+            if (SCALED) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(srcb + off[k]);
-            a0 = tri_accumulate(w, val);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(srcb + Ns + off[k]);
-            a1 = tri_accumulate(w, val);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(srcb + 2 * (size_t)Ns + off[k]);
-            a2 = tri_accumulate(w, val);
+                for (int c = 0; c < 3; ++c) { ra[c] = __fmul_rn(scale, ra[c]); rb[c] = __fmul_rn(scale, rb[c]); }
+            }
+            const uint32_t vox = vox0 + i * XS;
+            outb[vox] = __fadd_rn(a0, ra[0]);
+            outb[N + vox] = __fadd_rn(a1, ra[1]);
+            outb[2 * (size_t)N + vox] = __fadd_rn(a2, ra[2]);
+            if (hasB) {
+                outb[vox + XS] = __fadd_rn(b0, rb[0]);
+                outb[N + vox + XS] = __fadd_rn(b1, rb[1]);
+                outb[2 * (size_t)N + vox + XS] = __fadd_rn(b2, rb[2]);
+            }
         }
-        const uint32_t vox = ((uint32_t)x * Y + y) * Z + z;
-        outb[vox] = __fadd_rn(v0, __fmul_rn(scale, a0));
-        outb[N + vox] = __fadd_rn(v1, __fmul_rn(scale, a1));
-        outb[2 * (size_t)N + vox] = __fadd_rn(v2, __fmul_rn(scale, a2));
+    } else {
+        const float *srcb = src + (size_t)blockIdx.z * 3 * Ns;
+        const uint32_t GX = (uint32_t)Ys * Zs, GY = (uint32_t)Zs;
+        for (int i = 0; i < nx; ++i) {
+            float v0, v1, v2;                         // dynamic index -> select (keeps v[] in registers)
+#pragma unroll
+            for (int k = 0; k < TX; ++k)
+                if (k == i) { v0 = v[0][k]; v1 = v[1][k]; v2 = v[2][k]; }
+            const AxisF ax = axis_fast(__fadd_rn(fx0 + (float)i, v0), mxf, mxi);
+            const AxisF ay = axis_fast(__fadd_rn(fy, v1), myf, myi);
+            const AxisF az = axis_fast(__fadd_rn(fz, v2), mzf, mzi);
+            float w[8];
+            tri_weights(ax, ay, az, w);
+            float a[3];
+            if ((ax.i1 - ox < BX) && (ay.i1 - oy < BY) && (az.i1 - oz < BZ)) {
+                const float *q = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float val[8] = {q[c * CS], q[c * CS + 1], q[c * CS + PY], q[c * CS + PY + 1],
+                                          q[c * CS + PX], q[c * CS + PX + 1], q[c * CS + PX + PY], q[c * CS + PX + PY + 1]};
+                    a[c] = tri_accumulate(w, val);
+                }
+            } else {
+                const float *g = srcb + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float *gc = g + (size_t)c * Ns;
+                    const float val[8] = {__ldg(gc), __ldg(gc + 1), __ldg(gc + GY), __ldg(gc + GY + 1),
+                                          __ldg(gc + GX), __ldg(gc + GX + 1), __ldg(gc + GX + GY), __ldg(gc + GX + GY + 1)};
+                    a[c] = tri_accumulate(w, val);
+                }
+            }
+            if (SCALED) { a[0] = __fmul_rn(scale, a[0]); a[1] = __fmul_rn(scale, a[1]); a[2] = __fmul_rn(scale, a[2]); }
+            const uint32_t vox = vox0 + i * XS;
+            outb[vox] = __fadd_rn(v0, a[0]);
+            outb[N + vox] = __fadd_rn(v1, a[1]);
+            outb[2 * (size_t)N + vox] = __fadd_rn(v2, a[2]);
+        }
+    }
+}
+
+// =========================================================================================
+// one-channel image warp (linear)
+// =========================================================================================
+// FMODE: 0 = planar field, 1 = channels-last field, 2 = FUSED RescaleTransform: `field` is the
+// coarse planar field [B][3][Xh][Yh][Zh]; the displacement of every output voxel is resampled on
+// the fly from a shared-memory copy of the coarse box the tile touches (same arithmetic as
+// k_resize3_smem: pre-scaled values, reference corner order), so the full-resolution field is
+// never written to or read from HBM.
+struct UpsampleArgs {
+    const float *cx, *cy, *cz;      // sample coordinates of the output grid on the coarse grid
+    int Xh, Yh, Zh;
+    float pre;                      // vector scale applied before resampling (zoom factor)
+    int cap;                        // capacity (float4) of the coarse box in shared memory
+};
+
+template <int TX, int BX, int BY, int BZ, int FMODE>
+__global__ void __launch_bounds__(256)
+k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ img,
+             const float *__restrict__ field, float *__restrict__ out, int Xi, int Yi, int Zi, int X, int Y,
+             int Z, int has_fill, float fill, int nzt, UpsampleArgs up) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *brick = reinterpret_cast<float *>(smem_raw);   // [BX][BY][BZ]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_min[3], s_max[3];
+    constexpr int PX = BY * BZ, PY = BZ, CS = BX * BY * BZ;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
+    const int z = zt * TZ + lane, y = yt * TY + warp, x0 = blockIdx.y * TX;
+    const bool ok_yz = (z < Z) && (y < Y);
+    const uint32_t N = (uint32_t)X * Y * Z, Ni = (uint32_t)Xi * Yi * Zi;
+    const float *fb = field + (size_t)blockIdx.z * 3 * N;
+    float *outb = out + (size_t)blockIdx.z * N;
+    const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float fy = (float)y, fz = (float)z, fx0 = (float)x0;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + y) * Z + z, XS = (uint32_t)Y * Z;
+    const int nx = ok_yz ? min(TX, X - x0) : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        s_min[0] = s_min[1] = s_min[2] = INT_MAX;
+        s_max[0] = s_max[1] = s_max[2] = INT_MIN;
+    }
+    __syncthreads();
+
+    float l[3][TX];                                   // displacements, then sample locations
+    if (FMODE == 2) {
+        float4 *hbox = reinterpret_cast<float4 *>(smem_raw + (size_t)CS * sizeof(float));
+        const int Xh = up.Xh, Yh = up.Yh, Zh = up.Zh;
+        const uint32_t Nh = (uint32_t)Xh * Yh * Zh;
+        const float *hb = field + (size_t)blockIdx.z * 3 * Nh;
+        const int jx1 = min(x0 + TX, X) - 1, jy0 = yt * TY, jy1 = min(jy0 + TY, Y) - 1, jz0 = zt * TZ, jz1 = min(jz0 + TZ, Z) - 1;
+        // coarse box of the tile: [i1(first) - 1, i1(last)] per axis (tables are non-decreasing)
+        const int bx0 = axis_fast_i1(__ldg(up.cx + x0), (float)(Xh - 1), Xh - 1) - 1, bx1 = axis_fast_i1(__ldg(up.cx + jx1), (float)(Xh - 1), Xh - 1);
+        const int by0 = axis_fast_i1(__ldg(up.cy + jy0), (float)(Yh - 1), Yh - 1) - 1, by1 = axis_fast_i1(__ldg(up.cy + jy1), (float)(Yh - 1), Yh - 1);
+        const int bz0 = axis_fast_i1(__ldg(up.cz + jz0), (float)(Zh - 1), Zh - 1) - 1, bz1 = axis_fast_i1(__ldg(up.cz + jz1), (float)(Zh - 1), Zh - 1);
+        const int nbx = bx1 - bx0 + 1, nby = by1 - by0 + 1, nbz = bz1 - bz0 + 1;
+        const bool staged = nbx * nby * nbz <= up.cap;                   // CTA-uniform
+        if (staged) {
+            const int total = nbx * nby * nbz;
+            for (int t = threadIdx.x; t < total; t += 256) {
+                const int bz = t % nbz, q = t / nbz, by = q % nby, bx = q / nby;
+                const uint32_t o = ((uint32_t)(bx0 + bx) * Yh + (by0 + by)) * Zh + (bz0 + bz);
+                hbox[t] = make_float4(__fmul_rn(up.pre, __ldg(hb + o)), __fmul_rn(up.pre, __ldg(hb + Nh + o)),
+                                      __fmul_rn(up.pre, __ldg(hb + 2 * (size_t)Nh + o)), 0.f);
+            }
+        }
+        __syncthreads();
+        const AxisF ay = axis_fast(__ldg(up.cy + min(y, Y - 1)), (float)(Yh - 1), Yh - 1);
+        const AxisF az = axis_fast(__ldg(up.cz + min(z, Z - 1)), (float)(Zh - 1), Zh - 1);
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            l[0][i] = l[1][i] = l[2][i] = 0.f;
+            if (i < nx) {
+                const AxisF ax = axis_fast(__ldg(up.cx + x0 + i), (float)(Xh - 1), Xh - 1);
+                float w[8], v0[8], v1[8], v2[8];
+                tri_weights(ax, ay, az, w);
+                if (staged) {
+                    const int sy = nbz, sx = nby * nbz;
+                    const float4 *q = hbox + (((ax.i1 - 1 - bx0) * nby + (ay.i1 - 1 - by0)) * nbz + (az.i1 - 1 - bz0));
+                    const int o[8] = {0, 1, sy, sy + 1, sx, sx + 1, sx + sy, sx + sy + 1};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 t = q[o[k]];
+                        v0[k] = t.x; v1[k] = t.y; v2[k] = t.z;
+                    }
+                } else {
+                    const uint32_t gy = (uint32_t)Zh, gx = (uint32_t)Yh * Zh;
+                    const float *g = hb + ((uint32_t)(ax.i1 - 1) * gx + (uint32_t)(ay.i1 - 1) * gy + (uint32_t)(az.i1 - 1));
+                    gather8(g, gy, gx, 1u, v0);
+                    gather8(g + Nh, gy, gx, 1u, v1);
+                    gather8(g + 2 * (size_t)Nh, gy, gx, 1u, v2);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { v0[k] = __fmul_rn(up.pre, v0[k]); v1[k] = __fmul_rn(up.pre, v1[k]); v2[k] = __fmul_rn(up.pre, v2[k]); }
+                }
+                l[0][i] = tri_accumulate(w, v0);
+                l[1][i] = tri_accumulate(w, v1);
+                l[2][i] = tri_accumulate(w, v2);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            if (i < nx) {
+                const uint32_t vox = vox0 + i * XS;
+                if (FMODE == 1) {
+                    l[0][i] = __ldg(fb + (size_t)vox * 3); l[1][i] = __ldg(fb + (size_t)vox * 3 + 1); l[2][i] = __ldg(fb + (size_t)vox * 3 + 2);
+                } else {
+                    l[0][i] = __ldg(fb + vox); l[1][i] = __ldg(fb + N + vox); l[2][i] = __ldg(fb + 2 * (size_t)N + vox);
+                }
+            } else {
+                l[0][i] = l[1][i] = l[2][i] = 0.f;
+            }
+        }
+    }
+    BoxReduce box;
+    box.init();
+#pragma unroll
+    for (int i = 0; i < TX; ++i) {
+        l[0][i] = __fadd_rn(fx0 + (float)i, l[0][i]);
+        l[1][i] = __fadd_rn(fy, l[1][i]);
+        l[2][i] = __fadd_rn(fz, l[2][i]);
+        if (i < nx)
+            box.add(axis_fast_i1(l[0][i], mxf, mxi), axis_fast_i1(l[1][i], myf, myi), axis_fast_i1(l[2][i], mzf, mzi));
+    }
+    box.commit(s_min, s_max, lane);
+    __syncthreads();
+    const int ox = s_min[0], oy = s_min[1], oz = s_min[2] & ~3;
+    if (ox == INT_MAX) return;
+    const bool fits = (s_max[0] - ox < BX) && (s_max[1] - oy < BY) && (s_max[2] - oz < BZ);
+
+    if (fits) {                                       // a box that does not fit is not worth staging
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(CS * sizeof(float)));
+            tma_load_4d(brick, &tmap, &bar, oz, oy, ox, (int)blockIdx.z);
+        }
+        mbar_wait(&bar, 0);
+    }
+
+    const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
+    if (fits) {
+#pragma unroll
+        for (int i = 0; i < TX; i += 2) {
+            if (i >= nx) break;
+            const bool hasB = i + 1 < nx;
+            const float lxa = l[0][i], lya = l[1][i], lza = l[2][i];
+            const float lxb = hasB ? l[0][i + 1] : lxa, lyb = hasB ? l[1][i + 1] : lya, lzb = hasB ? l[2][i + 1] : lza;
+            const AxisF ax = axis_fast(lxa, mxf, mxi), ay = axis_fast(lya, myf, myi), az = axis_fast(lza, mzf, mzi);
+            const AxisF bx = axis_fast(lxb, mxf, mxi), by = axis_fast(lyb, myf, myi), bz = axis_fast(lzb, mzf, mzi);
+            float wA[8], wB[8];
+            tri_weights_pair(ax, ay, az, bx, by, bz, wA, wB);
+            const float *qa = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
+            const float *qb = brick + (bx.i1 * PX + by.i1 * PY + bz.i1 + cbase);
+            const float va[8] = {qa[0], qa[1], qa[PY], qa[PY + 1], qa[PX], qa[PX + 1], qa[PX + PY], qa[PX + PY + 1]};
+            const float vb[8] = {qb[0], qb[1], qb[PY], qb[PY + 1], qb[PX], qb[PX + 1], qb[PX + PY], qb[PX + PY + 1]};
+            float ra, rb;
+            tri_accumulate_pair(wA, wB, va, vb, ra, rb);
+            if (has_fill) {
+                if (lxa < 0.f || lxa > mxf || lya < 0.f || lya > myf || lza < 0.f || lza > mzf) ra = fill;
+                if (lxb < 0.f || lxb > mxf || lyb < 0.f || lyb > myf || lzb < 0.f || lzb > mzf) rb = fill;
+            }
+            outb[vox0 + i * XS] = ra;
+            if (hasB) outb[vox0 + (i + 1) * XS] = rb;
+        }
+    } else {
+        const float *ib = img + (size_t)blockIdx.z * Ni;
+        const uint32_t GX = (uint32_t)Yi * Zi, GY = (uint32_t)Zi;
+        for (int i = 0; i < nx; ++i) {
+            float lx, ly, lz;
+#pragma unroll
+            for (int k = 0; k < TX; ++k)
+                if (k == i) { lx = l[0][k]; ly = l[1][k]; lz = l[2][k]; }
+            const AxisF ax = axis_fast(lx, mxf, mxi), ay = axis_fast(ly, myf, myi), az = axis_fast(lz, mzf, mzi);
+            float w[8];
+            tri_weights(ax, ay, az, w);
+            float r;
+            {
+                const float *g = ib + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1));
+                const float val[8] = {__ldg(g), __ldg(g + 1), __ldg(g + GY), __ldg(g + GY + 1),
+                                      __ldg(g + GX), __ldg(g + GX + 1), __ldg(g + GX + GY), __ldg(g + GX + GY + 1)};
+                r = tri_accumulate(w, val);
+            }
+            if (has_fill && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) r = fill;
+            outb[vox0 + i * XS] = r;
+        }
     }
 }
 
@@ -216,48 +455,148 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool brick_eligible(const float *src, const float *own, const float *out, int Xs, int Ys, int Zs, int X,
-                    int Y, int Z, unsigned flags) {
-    if (flags & (DFM_FIELD_IN_CL | DFM_FIELD_OUT_CL)) return false;
-    static const bool disabled = getenv("DFM_NO_BRICK") != nullptr;
-    if (disabled) return false;
-    if (Zs % 4 != 0 || !aligned16(src)) return false;        // TMA: 16-byte global strides
-    if (Xs < 2 || Ys < 2 || Zs < 4) return false;
-    (void)own; (void)out; (void)X; (void)Y; (void)Z;
-    return encode_fn() != nullptr;
+static bool brick_disabled() {
+    static const bool d = getenv("DFM_NO_BRICK") != nullptr;   // debugging aid: force direct gathers
+    return d;
 }
 
-template <int BX, int BY, int BZ>
-static int launch_brick_t(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
-                          int Y, int Z, float scale, cudaStream_t st) {
-    CUtensorMap tmap;
-    const cuuint64_t dims[4] = {(cuuint64_t)Zs, (cuuint64_t)Ys, (cuuint64_t)Xs, (cuuint64_t)B * 3};
-    const cuuint64_t strides[3] = {(cuuint64_t)Zs * 4, (cuuint64_t)Ys * Zs * 4, (cuuint64_t)Xs * Ys * Zs * 4};
-    const cuuint32_t box[4] = {BZ, BY, BX, 3};
+// 4-D map over a planar [nvol][X][Y][Z] fp32 tensor with box {BZ, BY, BX, bc}
+static bool encode_map(CUtensorMap *tmap, const float *base, int nvol, int X, int Y, int Z, int bx, int by,
+                       int bz, int bc) {
+    const cuuint64_t dims[4] = {(cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)nvol};
+    const cuuint64_t strides[3] = {(cuuint64_t)Z * 4, (cuuint64_t)Y * Z * 4, (cuuint64_t)X * Y * Z * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bc};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)src, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return DFM_EUNSUPPORTED;          // caller falls back to direct gathers
+    return encode_fn()(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool tma_source_ok(const float *p, int X, int Y, int Z) {
+    // TMA: 16-byte aligned base and strides; the i1 - 1 addressing needs every axis >= 2
+    return !brick_disabled() && encode_fn() != nullptr && Z % 4 == 0 && aligned16(p) && X >= 2 && Y >= 2 && Z >= 4;
+}
+
+bool brick_eligible(const float *src, const float *own, const float *out, int Xs, int Ys, int Zs, int X,
+                    int Y, int Z, unsigned flags) {
+    (void)own; (void)out; (void)X; (void)Y; (void)Z;
+    if (flags & (DFM_FIELD_IN_CL | DFM_FIELD_OUT_CL)) return false;
+    return tma_source_ok(src, Xs, Ys, Zs);
+}
+
+template <int TX, int BX, int BY, int BZ>
+static int launch_ss_brick_t(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
+                             int Y, int Z, float scale, cudaStream_t st) {
+    CUtensorMap tmap;
+    if (!encode_map(&tmap, src, B * 3, Xs, Ys, Zs, BX, BY, BZ, 3)) return DFM_EUNSUPPORTED;
     constexpr size_t smem = 3ull * BX * BY * BZ * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ss_brick<BX, BY, BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_ss_brick<TX, BX, BY, BZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_ss_brick<TX, BX, BY, BZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_ss_brick smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
     dim3 grid(nzt * nyt, nxt, B), block(256);
-    if (getenv("DFM_BRICK_DEBUG")) fprintf(stderr, "dfm: k_ss_brick<%d,%d,%d> grid (%d,%d,%d) smem %zu scale %g\n", BX, BY, BZ, grid.x, grid.y, grid.z, smem, scale);
-    k_ss_brick<BX, BY, BZ><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, nzt);
+    if (scale == 1.f)
+        k_ss_brick<TX, BX, BY, BZ, false><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, nzt);
+    else
+        k_ss_brick<TX, BX, BY, BZ, true><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, nzt);
     return check_launch("k_ss_brick");
 }
 
 int launch_ss_brick(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
                     int Y, int Z, float scale, int large_box, cudaStream_t st) {
-    // z extent = 32 (tile) + 1 (upper corner) + 3 (origin alignment) + deformation slack
-    if (large_box) return launch_brick_t<12, 12, 52>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st);
-    return launch_brick_t<10, 10, 40>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st);
+    // x/y extent = 8 (tile) + 1 (upper corner) + 1 (straddle) + deformation slack;
+    // z pitch 64 = 32 + 1 + 1 + 3 (origin alignment) + slack, and bank-conflict free
+    static const int cfg = getenv("DFM_BRICK_CFG") ? atoi(getenv("DFM_BRICK_CFG")) : 0;     // tuning aid
+#define DFM_SS(TXv, SX, SY, SZ, LX, LY, LZ)                                                                  \
+    return large_box ? launch_ss_brick_t<TXv, LX, LY, LZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st) \
+                     : launch_ss_brick_t<TXv, SX, SY, SZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st)
+    switch (cfg) {
+        case 1: DFM_SS(4, 6, 10, 40, 8, 12, 48);
+        case 2: DFM_SS(4, 6, 10, 64, 8, 12, 64);
+        case 3: DFM_SS(8, 10, 10, 40, 12, 12, 48);
+        case 4: DFM_SS(8, 10, 10, 64, 12, 12, 64);
+        case 5: DFM_SS(2, 4, 10, 40, 6, 12, 48);
+        default: DFM_SS(4, 6, 12, 40, 8, 12, 48);
+    }
+#undef DFM_SS
+}
+
+template <int TX, int BX, int BY, int BZ>
+static int launch_warp_brick_t(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
+                               int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
+    CUtensorMap tmap;
+    if (!encode_map(&tmap, img, B, Xi, Yi, Zi, BX, BY, BZ, 1)) return DFM_EUNSUPPORTED;
+    constexpr size_t smem = (size_t)BX * BY * BZ * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    UpsampleArgs none = {};
+    if (flags & DFM_FIELD_IN_CL)
+        k_warp_brick<TX, BX, BY, BZ, 1><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, none);
+    else
+        k_warp_brick<TX, BX, BY, BZ, 0><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, none);
+    return check_launch("k_warp_brick");
+}
+
+// fused RescaleTransform(zoom >= 1) + one-channel linear warp
+template <int TX, int BX, int BY, int BZ>
+static int launch_rescale_warp_t(const float *img, const float *half, float *out, const float *cx, const float *cy,
+                                 const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y,
+                                 int Z, float pre, int has_fill, float fill, cudaStream_t st) {
+    CUtensorMap tmap;
+    if (!encode_map(&tmap, img, B, Xi, Yi, Zi, BX, BY, BZ, 1)) return DFM_EUNSUPPORTED;
+    auto ext = [](int tile, int n_in, int n_out) {
+        const double ratio = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
+        return (int)(tile * ratio) + 3;
+    };
+    UpsampleArgs up = {cx, cy, cz, Xh, Yh, Zh, pre, ext(TX, Xh, X) * ext(TY, Yh, Y) * ext(TZ, Zh, Z)};
+    const size_t smem = (size_t)BX * BY * BZ * sizeof(float) + (size_t)up.cap * sizeof(float4);
+    if (smem > 200 * 1024) return DFM_EUNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick(fused) smem attribute: %s", cudaGetErrorString(e));
+        configured = smem;
+    }
+    const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    k_warp_brick<TX, BX, BY, BZ, 2><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, up);
+    return check_launch("k_warp_brick(fused rescale)");
+}
+
+int launch_rescale_warp(const float *img, const float *half, float *out, const float *cx, const float *cy,
+                        const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
+                        float pre, int has_fill, float fill, cudaStream_t st) {
+    if (!tma_source_ok(img, Xi, Yi, Zi) || Xh < 2 || Yh < 2 || Zh < 2) return DFM_EUNSUPPORTED;
+    return launch_rescale_warp_t<4, 10, 16, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre,
+                                                 has_fill, fill, st);
+}
+
+int launch_warp_brick(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
+                      int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
+    static const bool direct = getenv("DFM_WARP_DIRECT") != nullptr;   // tuning aid
+    if (direct || (flags & DFM_LOC_ABSOLUTE)) return DFM_EUNSUPPORTED;
+    if (!tma_source_ok(img, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
+    static const int cfg = getenv("DFM_WARP_CFG") ? atoi(getenv("DFM_WARP_CFG")) : 0;
+    switch (cfg) {
+        case 1: return launch_warp_brick_t<8, 16, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 2: return launch_warp_brick_t<8, 16, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 3: return launch_warp_brick_t<4, 10, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 4: return launch_warp_brick_t<8, 14, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+    }
 }
 
 }  // namespace dfm

@@ -12,7 +12,7 @@
 namespace dfm {
 
 template <int ROWS, int INTERP, bool IN_CL, bool OUT_CL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, float *__restrict__ out,
                  int Xs, int Ys, int Zs, int X, int Y, int Z, float scale, FastDiv zdiv,
                  uint32_t plane_items) {
@@ -27,6 +27,9 @@ k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, f
     float *outb = out + (size_t)blockIdx.z * 3 * N;
     const float *s0 = srcb, *s1 = IN_CL ? srcb + 1 : srcb + Ns, *s2 = IN_CL ? srcb + 2 : srcb + 2 * (size_t)Ns;
     const float fx = (float)x, fz = (float)z;
+    const bool fast = Xs >= 2 && Ys >= 2 && Zs >= 2;                 // uniform
+    const uint32_t gy = (IN_CL ? 3u : 1u) * Zs, gx = gy * Ys;      // corner strides (elements)
+    const size_t cs = IN_CL ? 1 : Ns;                                // component stride
 
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -43,19 +46,30 @@ k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, f
         const float lx = __fadd_rn(fx, v0), ly = __fadd_rn((float)y, v1), lz = __fadd_rn(fz, v2);
         float a0, a1, a2;
         if (INTERP == DFM_LINEAR) {
-            uint32_t off[8];
-            float w[8];
-            tri_setup(lx, ly, lz, Xs, Ys, Zs, off, w);
-            float val[8];
+            float w[8], val[8];
+            if (fast) {
+                const uint32_t base = tri_setup_fast(lx, ly, lz, Xs, Ys, Zs, w);
+                const uint32_t es = IN_CL ? 3u : 1u;
+                const float *g = s0 + (size_t)base * es;
+                gather8(g, gy, gx, es, val);
+                a0 = tri_accumulate(w, val);
+                gather8(g + cs, gy, gx, es, val);
+                a1 = tri_accumulate(w, val);
+                gather8(g + 2 * cs, gy, gx, es, val);
+                a2 = tri_accumulate(w, val);
+            } else {
+                uint32_t off[8];
+                tri_setup(lx, ly, lz, Xs, Ys, Zs, off, w);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(s0 + (IN_CL ? off[k] * 3 : off[k]));
-            a0 = tri_accumulate(w, val);
+                for (int k = 0; k < 8; ++k) val[k] = __ldg(s0 + (IN_CL ? off[k] * 3 : off[k]));
+                a0 = tri_accumulate(w, val);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(s1 + (IN_CL ? off[k] * 3 : off[k]));
-            a1 = tri_accumulate(w, val);
+                for (int k = 0; k < 8; ++k) val[k] = __ldg(s1 + (IN_CL ? off[k] * 3 : off[k]));
+                a1 = tri_accumulate(w, val);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(s2 + (IN_CL ? off[k] * 3 : off[k]));
-            a2 = tri_accumulate(w, val);
+                for (int k = 0; k < 8; ++k) val[k] = __ldg(s2 + (IN_CL ? off[k] * 3 : off[k]));
+                a2 = tri_accumulate(w, val);
+            }
         } else {
             uint32_t o = ((uint32_t)axis_nearest(lx, Xs - 1) * Ys + axis_nearest(ly, Ys - 1)) * Zs + axis_nearest(lz, Zs - 1);
             if (IN_CL) o *= 3;

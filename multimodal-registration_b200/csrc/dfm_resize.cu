@@ -8,7 +8,7 @@
 namespace dfm {
 
 template <int ROWS, int INTERP, bool IN_CL, bool OUT_CL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_resize(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ cx,
          const float *__restrict__ cy, const float *__restrict__ cz, int C, int Xi, int Yi, int Zi,
          int Xo, int Yo, int Zo, float pre, float post, FastDiv zdiv, uint32_t plane_items) {

@@ -18,7 +18,7 @@ __device__ __forceinline__ void load_field1(const float *fb, uint32_t N, uint32_
 // Lanes own 32 consecutive z of one row (every gather touches 1-3 lines), a thread owns ROWS
 // consecutive rows (independent chains -> ILP).  ONE_CH specialises the C = 1 image warp.
 template <int ROWS, bool ONE_CH, bool FIELD_CL, bool IMG_CL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_warp_linear(const float *__restrict__ img, const float *__restrict__ field, float *__restrict__ out,
               int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, float fill,
               int abs_loc, FastDiv zdiv, uint32_t plane_items) {
@@ -32,6 +32,9 @@ k_warp_linear(const float *__restrict__ img, const float *__restrict__ field, fl
     const float *ib = img + (size_t)blockIdx.z * C * Ni;
     float *ob = out + (size_t)blockIdx.z * C * N;
     const float fx = (float)x, fz = (float)z;
+    const bool fast = Xi >= 2 && Yi >= 2 && Zi >= 2;                              // uniform
+    const uint32_t es = (!ONE_CH && IMG_CL) ? (uint32_t)C : 1u;                  // element stride
+    const uint32_t gy = es * Zi, gx = gy * Yi;
 
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -43,17 +46,30 @@ k_warp_linear(const float *__restrict__ img, const float *__restrict__ field, fl
         const float lx = abs_loc ? u0 : __fadd_rn(fx, u0);
         const float ly = abs_loc ? u1 : __fadd_rn((float)y, u1);
         const float lz = abs_loc ? u2 : __fadd_rn(fz, u2);
-        uint32_t off[8];
         float w[8];
-        tri_setup(lx, ly, lz, Xi, Yi, Zi, off, w);
         const bool oob = has_fill && oob3(lx, ly, lz, Xi, Yi, Zi);
-        if (ONE_CH) {
-            float val[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) val[k] = __ldg(ib + off[k]);
-            const float acc = tri_accumulate(w, val);
-            ob[vox] = oob ? fill : acc;
+        if (fast) {
+            const uint32_t base = tri_setup_fast(lx, ly, lz, Xi, Yi, Zi, w);
+            if (ONE_CH) {
+                float val[8];
+                gather8(ib + base, gy, gx, 1u, val);
+                const float acc = tri_accumulate(w, val);
+                ob[vox] = oob ? fill : acc;
+            } else {
+                const float *ic = IMG_CL ? ib + (size_t)base * C : ib + base;
+                float *oc = IMG_CL ? ob + (size_t)vox * C : ob + vox;
+                for (int c = 0; c < C; ++c) {
+                    float val[8];
+                    gather8(ic, gy, gx, es, val);
+                    const float acc = tri_accumulate(w, val);
+                    *oc = oob ? fill : acc;
+                    ic += IMG_CL ? 1 : Ni;
+                    oc += IMG_CL ? 1 : N;
+                }
+            }
         } else {
+            uint32_t off[8];
+            tri_setup(lx, ly, lz, Xi, Yi, Zi, off, w);
             const float *ic = ib;
             float *oc = IMG_CL ? ob + (size_t)vox * C : ob + vox;
             for (int c = 0; c < C; ++c) {
@@ -71,7 +87,7 @@ k_warp_linear(const float *__restrict__ img, const float *__restrict__ field, fl
 
 // ------------------------------- nearest -----------------------------------------------
 template <typename T, int ROWS, bool FIELD_CL, bool IMG_CL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_warp_nearest(const T *__restrict__ img, const float *__restrict__ field, T *__restrict__ out,
                int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, T fill,
                int abs_loc, FastDiv zdiv, uint32_t plane_items) {
@@ -167,6 +183,10 @@ extern "C" int dfm_warp_fwd(const void *img, const float *field, void *out, int 
     cudaStream_t st = (cudaStream_t)stream;
     if (interp == DFM_LINEAR) {
         DFM_REQUIRE(elem_size == 4, DFM_EINVAL, "dfm_warp_fwd: linear interpolation needs fp32 (elem_size 4), got %d", elem_size);
+        if (C == 1) {   // one channel: TMA-brick path (dfm_brick.cu), falls through if not applicable
+            int rc = launch_warp_brick((const float *)img, field, (float *)out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+            if (rc != DFM_EUNSUPPORTED) return rc;
+        }
         return launch_linear((const float *)img, field, (float *)out, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
     }
     DFM_REQUIRE(interp == DFM_NEAREST, DFM_EINVAL, "dfm_warp_fwd: interp %d", interp);
@@ -177,4 +197,24 @@ extern "C" int dfm_warp_fwd(const void *img, const float *field, void *out, int 
         case 8: return launch_nearest<uint64_t>(img, field, out, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, fill_bits, flags, st);
         default: return fail(DFM_EINVAL, "dfm_warp_fwd: elem_size %d not in {1,2,4,8}", elem_size);
     }
+}
+
+extern "C" int dfm_rescale_warp_fwd(const float *img, const float *coarse, float *out, const float *cx, const float *cy,
+                                    const float *cz, float *work, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh,
+                                    int X, int Y, int Z, float factor, int has_fill, float fill, void *stream) {
+    DFM_REQUIRE(B >= 0 && Xi >= 1 && Yi >= 1 && Zi >= 1 && Xh >= 1 && Yh >= 1 && Zh >= 1 && X >= 1 && Y >= 1 && Z >= 1,
+                DFM_EINVAL, "dfm_rescale_warp_fwd: bad shape");
+    DFM_REQUIRE(B <= 65535 && X <= 65535, DFM_EINVAL, "dfm_rescale_warp_fwd: B and X must be <= 65535");
+    DFM_REQUIRE((uint64_t)X * Y * Z < (1ull << 30) && (uint64_t)Xi * Yi * Zi < (1ull << 30), DFM_EINVAL,
+                "dfm_rescale_warp_fwd: volume too large (>= 2^30 voxels)");
+    DFM_REQUIRE(factor >= 1.f, DFM_EINVAL, "dfm_rescale_warp_fwd: factor %g < 1 (scale-then-resize order only)", factor);
+    if (B == 0) return DFM_OK;
+    DFM_REQUIRE(img && coarse && out && cx && cy && cz, DFM_EINVAL, "dfm_rescale_warp_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_rescale_warp(img, coarse, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, factor, has_fill, fill, st);
+    if (rc != DFM_EUNSUPPORTED) return rc;
+    DFM_REQUIRE(work, DFM_EUNSUPPORTED, "dfm_rescale_warp_fwd: fused kernel not applicable to this shape and no work buffer given");
+    rc = dfm_resize_fwd(coarse, work, cx, cy, cz, B, 3, Xh, Yh, Zh, X, Y, Z, factor, 1.f, DFM_LINEAR, 0u, stream);
+    if (rc) return rc;
+    return dfm_warp_fwd(img, work, out, B, 1, Xi, Yi, Zi, X, Y, Z, DFM_LINEAR, 4, has_fill, fill, 0, 0u, stream);
 }

@@ -393,6 +393,37 @@ def rescale_dense_transform(trf, factor, interp_method=LINEAR, out_layout='plana
     return resize(trf, factor, interp_method, pre=factor, post=1.0, out_layout=out_layout)
 
 
+def rescale_warp(img, coarse_field, factor, fill_value=None):
+    """Fused ``RescaleTransform(factor)`` + linear ``SpatialTransformer`` of a one-channel image
+    (dfm.h: dfm_rescale_warp_fwd): identical results to rescale_dense_transform followed by warp,
+    without materialising the full-resolution field.  Inference only (no autograd)."""
+    _require_cuda(img, 'img')
+    coarse_field = _check_field(coarse_field, 'coarse_field')
+    if img.dim() != 5 or img.shape[-1] != 1:
+        raise ValueError('rescale_warp: img must be [B, X, Y, Z, 1]')
+    if factor < 1:
+        raise ValueError('rescale_warp: factor must be >= 1')
+    img = img.float().contiguous()
+    coarse = to_layout(coarse_field.detach(), 'planar')
+    B, Xi, Yi, Zi, _ = img.shape
+    _, Xh, Yh, Zh, _ = coarse.shape
+    X, Y, Z = int(Xh * factor), int(Yh * factor), int(Zh * factor)
+    dev = img.device.index if img.device.index is not None else torch.cuda.current_device()
+    cx = _coords.device_tables(Xh, X, dev)[0]
+    cy = _coords.device_tables(Yh, Y, dev)[0]
+    cz = _coords.device_tables(Zh, Z, dev)[0]
+    out = torch.empty((B, X, Y, Z, 1), device=img.device, dtype=torch.float32)
+    has_fill = fill_value is not None
+    try:
+        _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(None),
+                  B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())
+    except _lib.DfmError:
+        work = torch.empty(B * 3 * X * Y * Z, device=img.device, dtype=torch.float32)
+        _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(work),
+                  B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------------------
 # Jacobian determinant
 # ---------------------------------------------------------------------------------------

@@ -2,9 +2,11 @@
 
 Bars (BASELINE.json north_star): nearest-neighbour warps bit-exact; trilinear warps and
 integrated fields within 1e-5 relative / 1e-4 voxel absolute; Jacobian determinants within
-1e-4.  The forward kernels keep the oracle's op order with separately rounded fp32 ops, so the
-linear paths are in fact checked for BIT-EXACT equality; gradients (atomics, FMA) use
-tolerances.
+1e-4.  Every test runs against both builds of the library: the exact-order build keeps the
+oracle's op order with separately rounded fp32 ops and is checked for BIT-EXACT equality on the
+linear paths; the default fused/packed build is checked against the north_star tolerance (it
+differs from the exact build only by removed intermediate roundings).  Gradients (atomics, FMA)
+use tolerances.
 """
 import glob
 import os
@@ -42,9 +44,19 @@ def smooth_noise(rng, shape, std, smooth=2):
     return (f / f.std() * std).astype(np.float32)
 
 
+@pytest.fixture(autouse=True, params=['fast', 'exact'])
+def arithmetic_mode(request):
+    """Every test runs against both builds: libdfm.so (fused/packed accumulation, the default
+    product) and libdfm_exact.so (reference op order, separately rounded ops)."""
+    mrb._lib.use(request.param == 'exact')
+    yield request.param
+    mrb._lib.use(False)
+
+
 def assert_linear_parity(got, want):
-    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
-    np.testing.assert_array_equal(got, want)      # stronger: same op order -> same bits
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)       # north_star bar, both builds
+    if mrb._lib.exact_order():
+        np.testing.assert_array_equal(got, want)  # exact build: same op order -> same bits
 
 
 # --------------------------------------------------------------------------------------
@@ -91,6 +103,35 @@ def test_warp_fill_value_linear_and_mismatched_grid():
         assert_linear_parity(got, want)
 
 
+@pytest.mark.parametrize('shape', [(1, 12, 16), (8, 1, 16), (8, 12, 1), (1, 1, 5), (2, 2, 4)])
+def test_degenerate_axes(shape):
+    # size-1 axes (2-D images embedded in 3-D): both corners alias the single voxel
+    rng = np.random.default_rng(77)
+    img = rng.random((2,) + shape + (2,)).astype(np.float32)
+    field = (rng.standard_normal((2,) + shape + (3,)) * 1.5).astype(np.float32)
+    for layout in ('cl', 'planar'):
+        assert_linear_parity(host(ops.warp(dev(img, layout), dev(field, layout))), io.spatial_transformer(img, field))
+        assert_linear_parity(host(ops.warp(dev(img[..., :1], layout), dev(field, layout))),
+                             io.spatial_transformer(img[..., :1], field))
+        assert_linear_parity(host(ops.vecint(dev(field, layout), 3)), io.vec_int(field, 3))
+    np.testing.assert_array_equal(host(ops.warp(dev(img), dev(field), 'nearest')),
+                                  io.spatial_transformer(img, field, 'nearest'))
+    want = io.rescale_dense_transform(field, 2)
+    assert_linear_parity(host(ops.rescale_dense_transform(dev(field, 'planar'), 2)), want)
+
+
+def test_strong_local_deformation_takes_the_checked_path():
+    # white-noise fields: the bounding box of a tile exceeds the brick -> per-thread fallback
+    rng = np.random.default_rng(78)
+    shape = (16, 16, 64)
+    field = (rng.standard_normal((2,) + shape + (3,)) * 6).astype(np.float32)
+    img = rng.random((2,) + shape + (1,)).astype(np.float32)
+    assert_linear_parity(host(ops.vecint(dev(field, 'planar'), 4)), io.vec_int(field, 4))
+    assert_linear_parity(host(ops.warp(dev(img), dev(field, 'planar'))), io.spatial_transformer(img, field))
+    assert_linear_parity(host(ops.warp(dev(img), dev(field, 'planar'), fill_value=0.5)),
+                         io.spatial_transformer(img, field, fill_value=0.5))
+
+
 def test_identity_and_translation_known_answers():
     rng = np.random.default_rng(3)
     img = rng.random((1, 8, 8, 8, 1)).astype(np.float32)
@@ -110,7 +151,7 @@ def test_transform_channelwise():
     want = io.transform(vol, shift)
     got = vxm.utils.transform(vol, shift)
     assert tuple(got.shape) == (X, Y, Z, C)
-    np.testing.assert_array_equal(host(got[None])[0], want)
+    assert_linear_parity(host(got[None])[0], want)
 
 
 def test_interpn_absolute_locations():
@@ -120,10 +161,10 @@ def test_interpn_absolute_locations():
     for method in ('linear', 'nearest'):
         want = io.interpn(vol, loc, method)
         got = ne.utils.interpn(vol, loc, method).cpu().numpy()
-        np.testing.assert_array_equal(got, want)
+        (assert_linear_parity if method == 'linear' else np.testing.assert_array_equal)(got, want)
     want = io.interpn(vol[..., 0], [loc[..., d] for d in range(3)], 'linear', fill_value=0.25)
     got = ne.utils.interpn(vol[..., 0], [loc[..., d] for d in range(3)], 'linear', fill_value=0.25).cpu().numpy()
-    np.testing.assert_array_equal(got, want)
+    assert_linear_parity(got, want)
 
 
 # --------------------------------------------------------------------------------------
@@ -150,9 +191,9 @@ def test_vecint_layer_and_integrate_vec():
     rng = np.random.default_rng(17)
     svf = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0)
     want = io.vec_int(svf, 5)
-    np.testing.assert_array_equal(host(vxm.layers.VecInt(int_steps=5)(svf)), want)
+    assert_linear_parity(host(vxm.layers.VecInt(int_steps=5)(svf)), want)
     got = vxm.utils.integrate_vec(svf[0], nb_steps=5)
-    np.testing.assert_array_equal(host(got[None])[0], want[0])
+    assert_linear_parity(host(got[None])[0], want[0])
 
 
 @pytest.mark.parametrize('layout', ['cl', 'planar'])
@@ -169,7 +210,7 @@ def test_compose(layout):
     np.testing.assert_array_equal(host(ops.compose([dev(a, layout), dev(b, layout)], 'nearest')), wantn)
     # the unbatched reference call (bids_two_steps_registration.py:324) + K.eval analogue
     got = vxm.utils.to_numpy(vxm.utils.compose([a[0], b[0]]))
-    np.testing.assert_array_equal(got, want[0])
+    assert_linear_parity(got, want[0])
     z = np.zeros_like(a)
     np.testing.assert_array_equal(host(ops.compose([dev(a), dev(z)])), a)
 
@@ -188,8 +229,8 @@ def test_rescale_dense_transform(shape, factor, layout):
     wantn = io.rescale_dense_transform(f, factor, 'nearest')
     np.testing.assert_array_equal(host(ops.rescale_dense_transform(dev(f, layout), factor, 'nearest')), wantn)
     # unbatched + batched dispatch of the reference function (3d_reg.py:394)
-    np.testing.assert_array_equal(host(vxm.utils.rescale_dense_transform(f, factor)), want)
-    np.testing.assert_array_equal(host(vxm.utils.rescale_dense_transform(f[0], factor)[None])[0], want[0])
+    assert_linear_parity(host(vxm.utils.rescale_dense_transform(f, factor)), want)
+    assert_linear_parity(host(vxm.utils.rescale_dense_transform(f[0], factor)[None])[0], want[0])
 
 
 def test_resize_any_channels():
@@ -197,7 +238,7 @@ def test_resize_any_channels():
     vol = rng.random((6, 8, 8, 5)).astype(np.float32)
     want = io.resize(vol, [2, 1.5, 0.5])
     got = host(ne.utils.resize(vol, [2, 1.5, 0.5])[None])[0]
-    np.testing.assert_array_equal(got, want)
+    assert_linear_parity(got, want)
 
 
 def test_transform_model_and_vxmdense_tail():
@@ -207,18 +248,36 @@ def test_transform_model_and_vxmdense_tail():
     for interp in ('linear', 'nearest'):
         want = io.transform_model(scan, half, interp, rescale=2)
         got = vxm.networks.Transform((8, 12, 16), interp_method=interp, rescale=2).predict([scan, half])
-        np.testing.assert_array_equal(got, want)
+        (assert_linear_parity if interp == 'linear' else np.testing.assert_array_equal)(got, want)
     full = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0)
     want = io.transform_model(scan, full, 'linear', rescale=1)       # 3d_reg.py:317,333: scale == 1
     got = vxm.networks.Transform((8, 12, 16), rescale=1).predict([scan, full])
-    np.testing.assert_array_equal(got, want)
+    assert_linear_parity(got, want)
     # VxmDense tail: svf at half res -> VecInt(5) -> x2 -> linear warp; second output = preint flow
+    fused = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2, fuse_rescale_warp=True)
     model = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2)
+    np.testing.assert_array_equal(fused.predict_deform([scan, half])[0], model.predict_deform([scan, half])[0])
+    assert fused.references.pos_flow is None
     y, pre = model.predict_deform([scan, half])
+    model.deform([scan, half])          # keeps references.pos_flow (predict_deform may fuse it away)
     flow = io.rescale_dense_transform(io.vec_int(half, 5), 2)
-    np.testing.assert_array_equal(y, io.spatial_transformer(scan, flow))
+    assert_linear_parity(y, io.spatial_transformer(scan, flow))
     np.testing.assert_array_equal(pre, half)
-    np.testing.assert_array_equal(host(model.references.pos_flow), flow)
+    assert_linear_parity(host(model.references.pos_flow), flow)
+
+
+def test_fused_rescale_warp_matches_unfused_bitwise():
+    rng = np.random.default_rng(61)
+    for shape, B in [((8, 12, 16), 2), ((20, 20, 48), 1), ((6, 5, 7), 1)]:
+        full = tuple(2 * s for s in shape)
+        half = smooth_noise(rng, (B,) + shape + (3,), 2.5, smooth=1)
+        scan = rng.random((B,) + full + (1,)).astype(np.float32)
+        for fv in (None, 0.0):
+            fused = host(ops.rescale_warp(dev(scan), dev(half, 'planar'), 2, fv))
+            flow = ops.rescale_dense_transform(dev(half, 'planar'), 2)
+            unfused = host(ops.warp(dev(scan), flow, 'linear', fv))
+            np.testing.assert_array_equal(fused, unfused)           # same arithmetic, either build
+            assert_linear_parity(fused, io.spatial_transformer(scan, io.rescale_dense_transform(half, 2), 'linear', fv))
 
 
 # --------------------------------------------------------------------------------------
