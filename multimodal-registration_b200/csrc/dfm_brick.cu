@@ -25,41 +25,9 @@
 #include <stdlib.h>
 
 #include "dfm_common.cuh"
+#include "dfm_tma.cuh"
 
 namespace dfm {
-
-// ------------------------------- PTX helpers ---------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    // bounded spin: a barrier that never completes traps instead of hanging the GPU
-    for (uint32_t it = 0; !mbar_try_wait(bar, phase); ++it)
-        if (it > (1u << 24)) __trap();
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 
 constexpr int TY = 8, TZ = 32;
 
@@ -434,47 +402,17 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 }
 
 // ------------------------------- host side -----------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
 static bool brick_disabled() {
     static const bool d = getenv("DFM_NO_BRICK") != nullptr;   // debugging aid: force direct gathers
     return d;
 }
-
-// 4-D map over a planar [nvol][X][Y][Z] fp32 tensor with box {BZ, BY, BX, bc}
 static bool encode_map(CUtensorMap *tmap, const float *base, int nvol, int X, int Y, int Z, int bx, int by,
                        int bz, int bc) {
-    const cuuint64_t dims[4] = {(cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)nvol};
-    const cuuint64_t strides[3] = {(cuuint64_t)Z * 4, (cuuint64_t)Y * Z * 4, (cuuint64_t)X * Y * Z * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, (cuuint32_t)bc};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return encode_fn()(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return encode_planar_map(tmap, base, nvol, X, Y, Z, bx, by, bz, bc);
 }
-
 static bool tma_source_ok(const float *p, int X, int Y, int Z) {
-    // TMA: 16-byte aligned base and strides; the i1 - 1 addressing needs every axis >= 2
-    return !brick_disabled() && encode_fn() != nullptr && Z % 4 == 0 && aligned16(p) && X >= 2 && Y >= 2 && Z >= 4;
+    // the i1 - 1 addressing needs every axis >= 2
+    return !brick_disabled() && tma_planar_ok(p, X, Y, Z) && X >= 2 && Y >= 2 && Z >= 4;
 }
 
 bool brick_eligible(const float *src, const float *own, const float *out, int Xs, int Ys, int Zs, int X,

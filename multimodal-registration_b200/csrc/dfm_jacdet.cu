@@ -2,7 +2,10 @@
 // 4th-order central differences on the interior [2:-2]^3, det(I + J) in fp64, fold count and
 // moments.  fp64 in registers is free under the memory roof; HBM sees the field once
 // (12 B/voxel as fp32) and the determinant map once.
+#include <cuda.h>
+
 #include "dfm_common.cuh"
+#include "dfm_tma.cuh"
 
 namespace dfm {
 
@@ -93,6 +96,138 @@ k_jacdet_finalize(const double *__restrict__ partials, double *__restrict__ stat
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path for planar fp32 fields: plane-marching tile kernel.
+// A CTA owns 32 x 16 x 32 (x, y, z) determinants.  It marches along x; every step the input
+// plane x+2 (16+4 rows x 32+4 columns x 3 components) is staged in a 4-slot shared-memory ring.
+// A thread owns two (y, z) columns: the x stencil comes from a 5-deep register window of its own
+// column, the y and z stencils from the shared plane.  The four-point stencil is evaluated in
+// fp32 in difference form  ((u[-2] - u[+2]) + 8 (u[+1] - u[-1]))  -- differences of neighbouring
+// samples, so the fp32 rounding is relative to the local variation of the field (~1e-7 for
+// registration fields) -- then converted once per derivative and the determinant, the fold test
+// and the moments are done in fp64.  (The all-fp64 kernel above needs 36 fp32->fp64 conversions
+// per voxel, which run at 1/8 rate; it is kept for fp64 inputs and channels-last fields.)
+// ---------------------------------------------------------------------------------------
+constexpr int JT_X = 32, JT_Y = 16, JT_Z = 32, JP_Y = JT_Y + 4, JP_Z = JT_Z + 4, J_SLOTS = 5;
+
+__device__ __forceinline__ float d4f(float m2, float m1, float p1, float p2) {
+    return fmaf(8.f, p1 - m1, m2 - p2);            // 12 * derivative
+}
+
+// TMA plane ring: one 4-D box {JP_Z, JP_Y, 1, 3} per input plane, J_SLOTS deep, one mbarrier per
+// slot.  A slot is re-armed only after the __syncthreads() that follows its last reader.
+template <typename Tout>
+__global__ void __launch_bounds__(256)
+k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det, double *__restrict__ partials,
+               int X, int Y, int Z, int nzt) {
+    // every slot starts on a 128-byte boundary (TMA destination alignment): 2160 floats padded to 2176
+    constexpr int SLOT_FLOATS = ((3 * JP_Y * JP_Z + 31) / 32) * 32;
+    __shared__ __align__(128) float plane_raw[J_SLOTS][SLOT_FLOATS];
+#define PL(slot, c, y, z) plane_raw[slot][((c) * JP_Y + (y)) * JP_Z + (z)]
+    __shared__ __align__(8) uint64_t bar[J_SLOTS];
+    constexpr uint32_t PLANE_BYTES = 3 * JP_Y * JP_Z * sizeof(float);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
+    const int zo0 = zt * JT_Z, yo0 = yt * JT_Y, xo0 = blockIdx.y * JT_X;
+    const int Xo = X - 4, Yo = Y - 4, Zo = Z - 4;
+    const int nxo = min(JT_X, Xo - xo0);                     // output planes of this CTA
+    const int np = nxo + 4;                                  // input planes
+    const int zo = zo0 + lane;
+    const bool okz = zo < Zo;
+    const bool oky0 = (yo0 + warp) < Yo, oky1 = (yo0 + warp + 8) < Yo;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < J_SLOTS; ++k) mbar_init(&bar[k], 1);
+    }
+    __syncthreads();
+    auto issue = [&](int p) {                                // thread 0 only
+        mbar_expect_tx(&bar[p % J_SLOTS], PLANE_BYTES);
+        tma_load_4d(&plane_raw[p % J_SLOTS][0], &tmap, &bar[p % J_SLOTS], zo0, yo0, xo0 + p, (int)blockIdx.z * 3);
+    };
+    if (threadIdx.x == 0)
+        for (int p = 0; p < min(np, J_SLOTS - 2); ++p) issue(p);
+
+    float win[3][2][5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) win[c][r][k] = 0.f;
+    double s = 0.0, s2 = 0.0, nn = 0.0;
+
+    // one step: plane p arrives, its centres enter the register window at position (p % 5), and if
+    // p >= 4 the determinants of output plane p - 4 (centre plane p - 2) are produced.  The window is
+    // indexed with compile-time rotations K = p % 5, so it never moves between registers.
+#define JAC_STEP(K)                                                                                                   \
+    if (p < np) {                                                                                                     \
+        const int slot = p % J_SLOTS;                                                                                 \
+        mbar_wait(&bar[slot], (uint32_t)((p / J_SLOTS) & 1));                                                         \
+        _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                               \
+            win[c][0][K] = PL(slot, c, warp + 2, lane + 2);                                                        \
+            win[c][1][K] = PL(slot, c, warp + 10, lane + 2);                                                       \
+        }                                                                                                             \
+        if (p >= 4) {                                                                                                 \
+            const int xo = xo0 + p - 4, cs = (p - 2) % J_SLOTS;                                                       \
+            _Pragma("unroll") for (int r = 0; r < 2; ++r) {                                                           \
+                if (okz && (r ? oky1 : oky0)) {                                                                       \
+                    const int yy = warp + 8 * r + 2, zz = lane + 2;                                                   \
+                    double J[3][3];                                                                                   \
+                    _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                   \
+                        const float dx = d4f(win[c][r][(K + 1) % 5], win[c][r][(K + 2) % 5], win[c][r][(K + 4) % 5], win[c][r][K]); \
+                        const float dy = d4f(PL(cs, c, yy - 2, zz), PL(cs, c, yy - 1, zz), PL(cs, c, yy + 1, zz), PL(cs, c, yy + 2, zz)); \
+                        const float dz = d4f(PL(cs, c, yy, zz - 2), PL(cs, c, yy, zz - 1), PL(cs, c, yy, zz + 1), PL(cs, c, yy, zz + 2)); \
+                        J[c][0] = (double)dx * (1.0 / 12.0);                                                          \
+                        J[c][1] = (double)dy * (1.0 / 12.0);                                                          \
+                        J[c][2] = (double)dz * (1.0 / 12.0);                                                          \
+                    }                                                                                                 \
+                    J[0][0] += 1.0; J[1][1] += 1.0; J[2][2] += 1.0;                                                   \
+                    const double dval = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -                           \
+                                        J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +                           \
+                                        J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);                            \
+                    if (det)                                                                                          \
+                        det[(size_t)blockIdx.z * Xo * Yo * Zo + ((size_t)xo * Yo + (yo0 + warp + 8 * r)) * Zo + zo] = (Tout)dval; \
+                    s += dval; s2 += dval * dval; nn += (dval < 0.0) ? 1.0 : 0.0;                                     \
+                }                                                                                                     \
+            }                                                                                                         \
+        }                                                                                                             \
+        __syncthreads();   /* every reader of plane p - 2's predecessor slots is done */                              \
+        if (threadIdx.x == 0 && p + J_SLOTS - 2 < np) issue(p + J_SLOTS - 2);                                         \
+        ++p;                                                                                                          \
+    }
+
+    int p = 0;
+    while (p < np) {
+        JAC_STEP(0) JAC_STEP(1) JAC_STEP(2) JAC_STEP(3) JAC_STEP(4)
+    }
+#undef JAC_STEP
+#undef PL
+    if (!partials) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        nn += __shfl_down_sync(0xffffffffu, nn, o);
+    }
+    __shared__ double sh[3][8];
+    if (lane == 0) { sh[0][warp] = nn; sh[1][warp] = s; sh[2][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += sh[threadIdx.x][k];
+        const size_t nblk = (size_t)gridDim.x * gridDim.y;
+        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[((size_t)blockIdx.z * 3 + threadIdx.x) * nblk + blk] = a;
+    }
+}
+
+static size_t jac_tiled_blocks(int X, int Y, int Z) {
+    const size_t nzt = (Z - 4 + JT_Z - 1) / JT_Z, nyt = (Y - 4 + JT_Y - 1) / JT_Y, nxt = (X - 4 + JT_X - 1) / JT_X;
+    return nzt * nyt * nxt;
+}
+
 template <typename Tin, typename Tout>
 static int launch_jacdet(const void *field, void *det, double *partials, int B, int X, int Y, int Z,
                          unsigned flags, cudaStream_t st) {
@@ -113,7 +248,8 @@ using namespace dfm;
 extern "C" size_t dfm_jacdet_workspace_bytes(int B, int X, int Y, int Z) {
     if (B <= 0 || X < 5 || Y < 5 || Z < 5) return 0;
     const size_t plane = (size_t)(Y - 4) * (Z - 4);
-    const size_t nblk = ((plane + 255) / 256) * (size_t)(X - 4);
+    size_t nblk = ((plane + 255) / 256) * (size_t)(X - 4);
+    if (jac_tiled_blocks(X, Y, Z) > nblk) nblk = jac_tiled_blocks(X, Y, Z);
     return (size_t)B * 3 * nblk * sizeof(double);
 }
 
@@ -130,13 +266,27 @@ extern "C" int dfm_jacdet(const void *field, void *det, double *stats, void *par
     cudaStream_t st = (cudaStream_t)stream;
     double *part = stats ? (double *)partials : nullptr;
     int rc;
-    if (in_f64) rc = out_f64 ? launch_jacdet<double, double>(field, det, part, B, X, Y, Z, flags, st)
-                             : launch_jacdet<double, float>(field, det, part, B, X, Y, Z, flags, st);
-    else        rc = out_f64 ? launch_jacdet<float, double>(field, det, part, B, X, Y, Z, flags, st)
-                             : launch_jacdet<float, float>(field, det, part, B, X, Y, Z, flags, st);
+    size_t nblk;
+    if (!in_f64 && !(flags & DFM_FIELD_IN_CL) && tma_planar_ok((const float *)field, X, Y, Z)) {
+        // planar fp32: plane-marching tile kernel
+        const int nzt = (Z - 4 + JT_Z - 1) / JT_Z, nyt = (Y - 4 + JT_Y - 1) / JT_Y, nxt = (X - 4 + JT_X - 1) / JT_X;
+        dim3 grid(nzt * nyt, nxt, B), block(256);
+        CUtensorMap tmap;
+        DFM_REQUIRE(encode_planar_map(&tmap, (const float *)field, B * 3, X, Y, Z, 1, JP_Y, JP_Z, 3), DFM_ECUDA,
+                    "dfm_jacdet: cuTensorMapEncodeTiled failed");
+        if (out_f64) k_jacdet_tiled<double><<<grid, block, 0, st>>>(tmap, (double *)det, part, X, Y, Z, nzt);
+        else k_jacdet_tiled<float><<<grid, block, 0, st>>>(tmap, (float *)det, part, X, Y, Z, nzt);
+        rc = check_launch("dfm_jacdet(tiled)");
+        nblk = jac_tiled_blocks(X, Y, Z);
+    } else {
+        if (in_f64) rc = out_f64 ? launch_jacdet<double, double>(field, det, part, B, X, Y, Z, flags, st)
+                                 : launch_jacdet<double, float>(field, det, part, B, X, Y, Z, flags, st);
+        else        rc = out_f64 ? launch_jacdet<float, double>(field, det, part, B, X, Y, Z, flags, st)
+                                 : launch_jacdet<float, float>(field, det, part, B, X, Y, Z, flags, st);
+        const size_t plane = (size_t)(Y - 4) * (Z - 4);
+        nblk = ((plane + 255) / 256) * (size_t)(X - 4);
+    }
     if (rc || !stats) return rc;
-    const size_t plane = (size_t)(Y - 4) * (Z - 4);
-    const size_t nblk = ((plane + 255) / 256) * (size_t)(X - 4);
     k_jacdet_finalize<<<B, 256, 0, st>>>(part, stats, nblk, (double)(X - 4) * (Y - 4) * (Z - 4));
     return check_launch("dfm_jacdet(finalize)");
 }

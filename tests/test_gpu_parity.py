@@ -295,23 +295,30 @@ def test_jacobian_against_reference_golden(path):
             det, stats = ops.jacobian_determinant(dev(field.astype(in_dtype), layout))
             det = det.cpu().numpy().reshape(-1)
             np.testing.assert_allclose(det, g['det'], rtol=0, atol=1e-4)       # north_star bar
-            np.testing.assert_allclose(det, g['det'], rtol=1e-12, atol=1e-12)  # what fp64 really gives
+            # fp64 inputs and channels-last fields take the all-fp64 kernel; planar fp32 fields the
+            # plane-marching kernel whose stencil differences are formed in fp32
+            tight = 1e-12 if (in_dtype == np.float64 or layout == 'cl') else 1e-5
+            np.testing.assert_allclose(det, g['det'], rtol=tight, atol=tight)
             n_neg, s, s2, n = stats.cpu().numpy()[0]
             assert int(n_neg) == int(g['n_neg']) and int(n) == g['det'].size
-            assert abs(s / n - float(g['mean'])) < 1e-12
-            assert abs(np.sqrt(max(s2 / n - (s / n) ** 2, 0)) - float(g['std'])) < 1e-9
+            assert abs(s / n - float(g['mean'])) < max(tight, 1e-12)
+            assert abs(np.sqrt(max(s2 / n - (s / n) ** 2, 0)) - float(g['std'])) < max(tight, 1e-9)
     det32, _ = ops.jacobian_determinant(dev(field), out_dtype=torch.float32, want_stats=False)
     np.testing.assert_allclose(det32.cpu().numpy().reshape(-1), g['det'], rtol=0, atol=1e-4)
 
 
 def test_jacobian_batched_and_oracle():
     rng = np.random.default_rng(37)
-    f = smooth_noise(rng, (3, 12, 10, 14, 3), 1.0)
+    f = smooth_noise(rng, (3, 40, 23, 37, 3), 1.0)      # several tiles with ragged edges
     det, stats = ops.jacobian_determinant(dev(f, 'planar'))
     for b in range(3):
         d, n = jo.jacobian_determinant(f[b][:, :, :, None, :])
-        np.testing.assert_allclose(det[b].cpu().numpy().reshape(-1), d, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(det[b].cpu().numpy().reshape(-1), d, rtol=1e-5, atol=1e-5)
         assert int(stats[b, 0].item()) == n
+    det64, _ = ops.jacobian_determinant(dev(f.astype(np.float64), 'planar'))
+    for b in range(3):
+        d, n = jo.jacobian_determinant(f[b][:, :, :, None, :])
+        np.testing.assert_allclose(det64[b].cpu().numpy().reshape(-1), d, rtol=1e-12, atol=1e-12)
 
 
 # --------------------------------------------------------------------------------------
