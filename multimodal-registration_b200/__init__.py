@@ -13,7 +13,7 @@ mirrors as ``voxelmorph`` and ``neurite`` so ``import voxelmorph as vxm`` resolv
 """
 import sys
 
-from . import _lib, ops          # noqa: F401
+from . import _lib, ops, sharding          # noqa: F401
 from . import neurite, voxelmorph   # noqa: F401
 
 __version__ = '0.1.0'

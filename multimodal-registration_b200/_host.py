@@ -62,3 +62,30 @@ def to_host(t, tag='out', copy=True):
     stage.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return stage.numpy().copy() if copy else stage.numpy()
+
+
+_STREAMS = {}
+
+
+def side_streams():
+    """Two cached non-default streams per device (H2D copies, D2H copies)."""
+    idx = torch.cuda.current_device()
+    if idx not in _STREAMS:
+        _STREAMS[idx] = (torch.cuda.Stream(), torch.cuda.Stream())
+    return _STREAMS[idx]
+
+
+def pinned_view(x, dtype, tag):
+    """Host array / tensor -> pinned CPU tensor of ``dtype`` (no copy if it already is one)."""
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.is_pinned() and t.is_contiguous():
+        return t
+    stage = _pinned(t.shape, t.dtype, tag)
+    stage.copy_(t)
+    return stage
+
+
+def pinned_out(shape, dtype, tag):
+    return _pinned(shape, dtype, tag)

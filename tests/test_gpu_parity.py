@@ -266,6 +266,22 @@ def test_transform_model_and_vxmdense_tail():
     assert_linear_parity(host(model.references.pos_flow), flow)
 
 
+def test_chunked_predict_equals_single_call():
+    rng = np.random.default_rng(67)
+    scan = rng.random((5, 8, 12, 16, 1)).astype(np.float32)
+    half = smooth_noise(rng, (5, 4, 6, 8, 3), 1.5, smooth=1)
+    model = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2)
+    y1, p1 = model.predict_deform([scan, half], batch_size=8)          # one call
+    y2, p2 = model.predict_deform([scan, half], batch_size=2)          # 3 chunks on side streams
+    np.testing.assert_array_equal(y1, y2)
+    np.testing.assert_array_equal(p1, half)
+    np.testing.assert_array_equal(p2, half)
+    warp = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2, reg_field='warp')
+    y3, w3 = warp.predict_deform([scan, half], batch_size=2)
+    np.testing.assert_array_equal(y3, y1)
+    assert_linear_parity(w3, io.rescale_dense_transform(io.vec_int(half, 5), 2))
+
+
 def test_fused_rescale_warp_matches_unfused_bitwise():
     rng = np.random.default_rng(61)
     for shape, B in [((8, 12, 16), 2), ((20, 20, 48), 1), ((6, 5, 7), 1)]:
