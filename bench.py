@@ -298,7 +298,10 @@ def run_own(args):
                     'api': 'voxelmorph.networks.VxmDense(...).predict_deform([source, flow]) on pinned host arrays'},
             'gpu_launches': args.steps * (INT_STEPS + 2),
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': dom['achieved_gbs'], 'peak': peak,
-                         'unit': 'GB/s', 'frac': dom['frac_of_peak'], 'traffic': TRAFFIC_NCU.get(dom_name),
+                         'unit': 'GB/s', 'frac': dom['frac_of_peak'],
+                         'traffic': (TRAFFIC_NCU_PER_PAIR[dom_name] * B / 1e9) if dom_name in TRAFFIC_NCU_PER_PAIR else None,
+                         'traffic_unit': 'GB per launch (ncu dram read+write at B=8, scaled to this batch)',
+                         'achieved_bytes_per_launch_GB': dom['algorithmic_bytes_per_launch'] / 1e9,
                          'peak_source': peak_src,
                          'pipeline_achieved': B * (INT_STEPS * BYTES_SS_STEP + BYTES_RESCALE + BYTES_WARP)
                          / (ms_per_step * 1e-3) / 1e9},
@@ -313,9 +316,13 @@ def run_own(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# capture (profiles/); None until a capture of the current kernels exists.
-TRAFFIC_NCU = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch PER VOLUME PAIR, from the committed
+# `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
+TRAFFIC_NCU_PER_PAIR = {
+    'ss_step(k_ss_brick)': (59.004e6 + 22.844e6) / 8,
+    'rescale_x2(k_resize3_smem)': (59.011e6 + 414.804e6) / 8,
+    'warp_linear(k_warp_brick)': (629.045e6 + 143.886e6) / 8,
+}
 
 
 def main():
