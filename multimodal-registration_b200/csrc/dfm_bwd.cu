@@ -149,10 +149,14 @@ extern "C" int dfm_warp_bwd(const float *gout, const float *img, const float *fi
     if (B == 0 || (!gimg && !gfield)) return DFM_OK;
     DFM_REQUIRE(gout && img && field, DFM_EINVAL, "dfm_warp_bwd: null pointer");
     if (C == 1) flags &= ~DFM_IMG_CL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!gimg && gfield && flags == 0u) {     // d/dfield only, all planar: TMA channel ring, no atomics
+        int rc = launch_warp_mc_bwd_field(gout, img, field, gfield, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, st);
+        if (rc != DFM_EUNSUPPORTED) return rc;
+    }
     const uint32_t plane = (uint32_t)Y * Z;
     dim3 grid((plane + 255) / 256, X, B), block(256);
     FastDiv fd = make_fastdiv(Z);
-    cudaStream_t st = (cudaStream_t)stream;
     const int key = ((flags & DFM_FIELD_IN_CL) ? 4 : 0) | ((flags & DFM_FIELD_OUT_CL) ? 2 : 0) | ((flags & DFM_IMG_CL) ? 1 : 0);
 #define DFM_GO(F, G, I) k_warp_bwd<F, G, I><<<grid, block, 0, st>>>(gout, img, field, gimg, gfield, C, Xi, Yi, Zi, X, Y, Z, has_fill, fd, plane)
     switch (key) {

@@ -41,6 +41,12 @@ int launch_rescale_warp(const float *img, const float *half, float *out, const f
                         const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
                         float pre, int has_fill, float fill, cudaStream_t st);
 
+// multi-channel planar linear warp through a TMA channel ring -- dfm_brick_mc.cu
+int launch_warp_mc_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
+                       int Y, int Z, int has_fill, float fill, cudaStream_t st);
+int launch_warp_mc_bwd_field(const float *gout, const float *img, const float *field, float *gfield, int B, int C,
+                             int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, cudaStream_t st);
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // n / d for n*d < 2^32 via one umulhi (host checks the range)

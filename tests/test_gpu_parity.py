@@ -363,6 +363,22 @@ def test_warp_backward(C, layout, fill):
     np.testing.assert_allclose(host(tf_.grad), gf, rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('shape,C,std', [((6, 8, 10), 5, 2.5), ((12, 20, 40), 7, 3.0), ((9, 9, 36), 3, 9.0)])
+@pytest.mark.parametrize('fill', [None, 0.0])
+def test_warp_backward_field_only_planar_multichannel(shape, C, std, fill):
+    # the `pred` gradient of the training step: planar C-channel image without gradient, d/dfield only
+    rng = np.random.default_rng(71)
+    img = rng.random((2,) + shape + (C,))
+    field = smooth_noise(rng, (2,) + shape + (3,), std).astype(np.float64)
+    g, (_, gf) = _grads_oracle(lambda i, f: to.spatial_transformer(i, f, 'linear', fill), img, field)
+    ti = dev(img.astype(np.float32), 'planar')
+    tf_ = dev(field.astype(np.float32), 'planar').requires_grad_(True)
+    out = ops.warp(ti, tf_, 'linear', fill)
+    assert_linear_parity(host(out.detach()), io.spatial_transformer(img.astype(np.float32), field.astype(np.float32), 'linear', fill))
+    out.backward(dev(g, 'planar'))
+    np.testing.assert_allclose(host(tf_.grad), gf, rtol=2e-4, atol=5e-5)
+
+
 @pytest.mark.parametrize('nsteps', [1, 3, 5])
 def test_vecint_backward(nsteps):
     rng = np.random.default_rng(43)
