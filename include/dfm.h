@@ -152,13 +152,16 @@ int dfm_ss_step_bwd(const float *g, const float *v, float *gv,
 int dfm_resize_fwd(const float *in, float *out, const float *cx, const float *cy, const float *cz,
                    int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
                    float pre, float post, int interp, unsigned flags, void *stream);
-/* Adjoint of the linear dfm_resize_fwd: gin[b,c,i] = pre*post * sum_j W[j,i] gout[b,c,j],
- * written as a gather (no atomics).  Planar only.
- * lo/hi: DEVICE int arrays (per axis, length n_in): output index range [lo, hi) whose
- * interpolation support touches input index i (computed by the host from cx/cy/cz). */
-int dfm_resize_bwd(const float *gout, float *gin, const float *cx, const float *cy, const float *cz,
-                   const int *xlo, const int *xhi, const int *ylo, const int *yhi,
-                   const int *zlo, const int *zhi,
+/* Adjoint of the linear dfm_resize_fwd, written as a gather (no atomics).  Planar only.
+ *   gin[b,c,i] = pre*post * sum_kx sum_ky sum_kz xw[ix][kx] yw[iy][ky] zw[iz][kz] *
+ *                gout[b,c, xlo[ix]+kx, ylo[iy]+ky, zlo[iz]+kz]
+ * Per axis (DEVICE arrays, computed by the host from cx/cy/cz): lo[n_in] = first output index
+ * whose interpolation support touches input i, cnt[n_in] = number of such outputs (contiguous),
+ * w[n_in][k] = the weight output lo[i]+k puts on input i (row length k = kx/ky/kz). */
+int dfm_resize_bwd(const float *gout, float *gin,
+                   const int *xlo, const int *xcnt, const float *xw, int kx,
+                   const int *ylo, const int *ycnt, const float *yw, int ky,
+                   const int *zlo, const int *zcnt, const float *zw, int kz,
                    int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
                    float pre, float post, void *stream);
 

@@ -39,6 +39,44 @@ def support_ranges(coords, n_in):
     return lo, hi
 
 
+def adjoint_taps(coords, n_in):
+    """(lo[n_in] int32, cnt[n_in] int32, w[n_in, kmax] float32): output j = lo[i] + k puts weight
+    w[i, k] on input i (k < cnt[i]); weights follow the forward kernel's axis set-up exactly."""
+    c = np.asarray(coords, np.float32)
+    maxf = np.float32(n_in - 1)
+    cl = np.clip(c, np.float32(0), maxf)
+    i1 = np.minimum(np.floor(cl).astype(np.int64) + 1, n_in - 1)
+    i0 = np.maximum(i1 - 1, 0)
+    w0 = (i1.astype(np.float32) - cl).astype(np.float32)       # weight of the lower corner
+    w1 = (np.float32(1) - w0).astype(np.float32)
+    lo = np.zeros(n_in, np.int32)
+    cnt = np.zeros(n_in, np.int32)
+    taps = [[] for _ in range(n_in)]
+    for j in range(len(c)):
+        taps[i0[j]].append((j, w0[j]))
+        if i1[j] != i0[j]:
+            taps[i1[j]].append((j, w1[j]))
+        else:
+            taps[i1[j]][-1] = (j, np.float32(w0[j] + w1[j]))
+    kmax = max(1, max(len(t) for t in taps))
+    w = np.zeros((n_in, kmax), np.float32)
+    for i, t in enumerate(taps):
+        if not t:
+            continue
+        js = [a for a, _ in t]
+        assert js == list(range(js[0], js[0] + len(js))), 'taps of a monotone grid are contiguous'
+        lo[i], cnt[i] = js[0], len(js)
+        w[i, :len(js)] = [b for _, b in t]
+    return lo, cnt, w
+
+
+@functools.lru_cache(maxsize=256)
+def device_adjoint_taps(n_in, n_out, device_index):
+    dev = torch.device('cuda', device_index)
+    lo, cnt, w = adjoint_taps(linspace_tf(n_in, n_out), n_in)
+    return (torch.from_numpy(lo).to(dev), torch.from_numpy(cnt).to(dev), torch.from_numpy(w).to(dev), int(w.shape[1]))
+
+
 @functools.lru_cache(maxsize=256)
 def device_tables(n_in, n_out, device_index):
     dev = torch.device('cuda', device_index)

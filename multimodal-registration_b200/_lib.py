@@ -31,7 +31,7 @@ SIGNATURES = {
     'dfm_vecint_bwd': (_i, [_p] * 4 + [_i] * 5 + [_p]),
     'dfm_ss_step_bwd': (_i, [_p] * 3 + [_i] * 4 + [_f, _p]),
     'dfm_resize_fwd': (_i, [_p] * 5 + [_i] * 8 + [_f, _f, _i, _u, _p]),
-    'dfm_resize_bwd': (_i, [_p] * 11 + [_i] * 8 + [_f, _f, _p]),
+    'dfm_resize_bwd': (_i, [_p, _p] + [_p, _p, _p, _i] * 3 + [_i] * 8 + [_f, _f, _p]),
     'dfm_jacdet_workspace_bytes': (_z, [_i] * 4),
     'dfm_jacdet': (_i, [_p] * 4 + [_i] * 6 + [_u, _p]),
     'dfm_cl_to_planar': (_i, [_p, _p, _i, _i, _z, _i, _p]),

@@ -221,23 +221,17 @@ static int launch_resize3_smem(const float *in, float *out, const float *cx, con
 }
 
 // ---------------------------------------------------------------------------------------
-// adjoint (gather form): gin[i] = pre*post * sum_{jx in Rx(ix)} sum_{jy} sum_{jz} wx wy wz gout[j]
-// where wa(j, i) = weight that output j puts on input index i along axis a.
+// adjoint (gather form, no atomics):
+//   gin[i] = pre*post * sum_{kx} wx[ix][kx] sum_{ky} wy[iy][ky] sum_{kz} wz[iz][kz] gout[xlo+kx, ylo+ky, zlo+kz]
+// The per-axis tap tables (first output index, tap count, weights) are computed by the host from
+// the same coordinate tables the forward kernel uses (`_coords.adjoint_taps`).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float axis_weight_on(float loc, float maxf, int i) {
-    const Axis a = axis_linear(loc, maxf);
-    float w = 0.f;
-    if (a.i0 == i) w += a.w0;
-    if (a.i1 == i) w += a.w1;
-    return w;
-}
-
 __global__ void __launch_bounds__(128)
-k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const float *__restrict__ cx,
-             const float *__restrict__ cy, const float *__restrict__ cz, const int *__restrict__ xlo,
-             const int *__restrict__ xhi, const int *__restrict__ ylo, const int *__restrict__ yhi,
-             const int *__restrict__ zlo, const int *__restrict__ zhi, int C, int Xi, int Yi, int Zi,
-             int Xo, int Yo, int Zo, float s, FastDiv zdiv, uint32_t plane_items) {
+k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const int *__restrict__ xlo,
+             const int *__restrict__ xcnt, const float *__restrict__ xw, int kx, const int *__restrict__ ylo,
+             const int *__restrict__ ycnt, const float *__restrict__ yw, int ky, const int *__restrict__ zlo,
+             const int *__restrict__ zcnt, const float *__restrict__ zw, int kz, int Xi, int Yi, int Zi, int Xo,
+             int Yo, int Zo, float s, FastDiv zdiv, uint32_t plane_items) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plane_items) return;
     const uint32_t iy = fast_div(p, zdiv);
@@ -246,18 +240,19 @@ k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const floa
     const uint32_t bc = blockIdx.z;   // b*C + c
     const size_t No = (size_t)Xo * Yo * Zo, Ni = (size_t)Xi * Yi * Zi;
     const float *gb = gout + (size_t)bc * No;
-    const int x0 = xlo[ix], x1 = xhi[ix], y0 = ylo[iy], y1 = yhi[iy], z0 = zlo[iz], z1 = zhi[iz];
+    const int x0 = __ldg(xlo + ix), nx = __ldg(xcnt + ix), y0 = __ldg(ylo + iy), ny = __ldg(ycnt + iy);
+    const int z0 = __ldg(zlo + iz), nz = __ldg(zcnt + iz);
     float acc = 0.f;
-    for (int jx = x0; jx < x1; ++jx) {
-        const float wx = axis_weight_on(__ldg(cx + jx), (float)(Xi - 1), ix);
-        for (int jy = y0; jy < y1; ++jy) {
-            const float wxy = wx * axis_weight_on(__ldg(cy + jy), (float)(Yi - 1), iy);
-            const float *row = gb + ((size_t)jx * Yo + jy) * Zo;
+    for (int a = 0; a < nx; ++a) {
+        const float wx = __ldg(xw + ix * kx + a);
+        float accy = 0.f;
+        for (int b = 0; b < ny; ++b) {
+            const float *row = gb + ((size_t)(x0 + a) * Yo + (y0 + b)) * Zo + z0;
             float accz = 0.f;
-            for (int jz = z0; jz < z1; ++jz)
-                accz = fmaf(axis_weight_on(__ldg(cz + jz), (float)(Zi - 1), iz), __ldg(row + jz), accz);
-            acc = fmaf(wxy, accz, acc);
+            for (int c = 0; c < nz; ++c) accz = fmaf(__ldg(zw + iz * kz + c), __ldg(row + c), accz);
+            accy = fmaf(__ldg(yw + iy * ky + b), accz, accy);
         }
+        acc = fmaf(wx, accy, acc);
     }
     gin[(size_t)bc * Ni + ((size_t)ix * Yi + iy) * Zi + iz] = s * acc;
 }
@@ -291,22 +286,23 @@ extern "C" int dfm_resize_fwd(const float *in, float *out, const float *cx, cons
     return launch_resize<DFM_NEAREST>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
 }
 
-extern "C" int dfm_resize_bwd(const float *gout, float *gin, const float *cx, const float *cy, const float *cz,
-                              const int *xlo, const int *xhi, const int *ylo, const int *yhi, const int *zlo,
-                              const int *zhi, int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
+extern "C" int dfm_resize_bwd(const float *gout, float *gin, const int *xlo, const int *xcnt, const float *xw, int kx,
+                              const int *ylo, const int *ycnt, const float *yw, int ky, const int *zlo, const int *zcnt,
+                              const float *zw, int kz, int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
                               float pre, float post, void *stream) {
     DFM_REQUIRE(B >= 0 && C >= 1 && Xi >= 1 && Yi >= 1 && Zi >= 1 && Xo >= 0 && Yo >= 0 && Zo >= 0, DFM_EINVAL,
                 "dfm_resize_bwd: bad shape");
+    DFM_REQUIRE(kx >= 1 && ky >= 1 && kz >= 1, DFM_EINVAL, "dfm_resize_bwd: tap counts must be >= 1");
     DFM_REQUIRE((uint64_t)B * C <= 65535 && Xi <= 65535, DFM_EINVAL, "dfm_resize_bwd: B*C and Xi must be <= 65535");
     DFM_REQUIRE((uint64_t)Xo * Yo * Zo < (1ull << 31) && (uint64_t)Xi * Yi * Zi < (1ull << 31), DFM_EINVAL,
                 "dfm_resize_bwd: volume too large");
     DFM_REQUIRE((uint64_t)Yi * Zi * (uint64_t)Zi < (1ull << 32), DFM_EINVAL, "dfm_resize_bwd: Yi*Zi*Zi must be < 2^32");
     if (B == 0) return DFM_OK;
-    DFM_REQUIRE(gout && gin && cx && cy && cz && xlo && xhi && ylo && yhi && zlo && zhi, DFM_EINVAL,
+    DFM_REQUIRE(gout && gin && xlo && xcnt && xw && ylo && ycnt && yw && zlo && zcnt && zw, DFM_EINVAL,
                 "dfm_resize_bwd: null pointer");
     const uint32_t plane = (uint32_t)Yi * Zi;
     dim3 grid((plane + 127) / 128, Xi, B * C), block(128);
-    k_resize_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(gout, gin, cx, cy, cz, xlo, xhi, ylo, yhi, zlo, zhi, C,
-                                                          Xi, Yi, Zi, Xo, Yo, Zo, pre * post, make_fastdiv(Zi), plane);
+    k_resize_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(gout, gin, xlo, xcnt, xw, kx, ylo, ycnt, yw, ky, zlo, zcnt, zw,
+                                                          kz, Xi, Yi, Zi, Xo, Yo, Zo, pre * post, make_fastdiv(Zi), plane);
     return check_launch("dfm_resize_bwd");
 }

@@ -358,11 +358,12 @@ class _ResizeLinear(torch.autograd.Function):
         Xo, Yo, Zo = ctx.out_shape
         gout = to_layout(gout.float(), 'planar')
         dev = gout.device.index
-        tx, ty, tz = (_coords.device_tables(Xi, Xo, dev), _coords.device_tables(Yi, Yo, dev),
-                      _coords.device_tables(Zi, Zo, dev))
+        tx, ty, tz = (_coords.device_adjoint_taps(Xi, Xo, dev), _coords.device_adjoint_taps(Yi, Yo, dev),
+                      _coords.device_adjoint_taps(Zi, Zo, dev))
         gin = empty(ctx.in_shape, 'planar', gout.device)
-        _lib.call('dfm_resize_bwd', _ptr(gout), _ptr(gin), _ptr(tx[0]), _ptr(ty[0]), _ptr(tz[0]),
-                  _ptr(tx[1]), _ptr(tx[2]), _ptr(ty[1]), _ptr(ty[2]), _ptr(tz[1]), _ptr(tz[2]),
+        _lib.call('dfm_resize_bwd', _ptr(gout), _ptr(gin),
+                  _ptr(tx[0]), _ptr(tx[1]), _ptr(tx[2]), tx[3], _ptr(ty[0]), _ptr(ty[1]), _ptr(ty[2]), ty[3],
+                  _ptr(tz[0]), _ptr(tz[1]), _ptr(tz[2]), tz[3],
                   B, C, Xi, Yi, Zi, Xo, Yo, Zo, float(ctx.pre), float(ctx.post), _stream())
         return gin, None, None, None
 

@@ -79,6 +79,26 @@ def test_support_ranges_cover_exactly_the_taps():
                 assert lo[i] == hi[i]
 
 
+def test_adjoint_taps_are_the_transpose_of_the_forward_weights():
+    for n_in, n_out in [(8, 16), (80, 160), (16, 8), (5, 13), (6, 6), (1, 4), (4, 1)]:
+        c = _coords.linspace_tf(n_in, n_out)
+        lo, cnt, w = _coords.adjoint_taps(c, n_in)
+        A = np.zeros((n_out, n_in))
+        cl = np.clip(c, 0, n_in - 1)
+        i1 = np.minimum(np.floor(cl).astype(int) + 1, n_in - 1)
+        i0 = np.maximum(i1 - 1, 0)
+        w0 = (i1.astype(np.float32) - cl).astype(np.float32)
+        for j in range(n_out):
+            A[j, i0[j]] += w0[j]
+            A[j, i1[j]] += np.float32(1) - w0[j]
+        Bm = np.zeros_like(A)
+        for i in range(n_in):
+            for k in range(cnt[i]):
+                Bm[lo[i] + k, i] = w[i, k]
+        np.testing.assert_allclose(A, Bm, atol=1e-7)
+        np.testing.assert_allclose(A.sum(1), 1.0, atol=1e-6)        # every output is a convex combination
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
 def test_no_cpu_fallback():
     vxm = mrb.voxelmorph
