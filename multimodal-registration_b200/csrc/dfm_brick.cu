@@ -380,21 +380,15 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     } else {
         const float *ib = img + (size_t)blockIdx.z * Ni;
         const uint32_t GX = (uint32_t)Yi * Zi, GY = (uint32_t)Zi;
-        for (int i = 0; i < nx; ++i) {
-            float lx, ly, lz;
 #pragma unroll
-            for (int k = 0; k < TX; ++k)
-                if (k == i) { lx = l[0][k]; ly = l[1][k]; lz = l[2][k]; }
+        for (int i = 0; i < TX; ++i) {
+            if (i >= nx) break;
+            const float lx = l[0][i], ly = l[1][i], lz = l[2][i];
             const AxisF ax = axis_fast(lx, mxf, mxi), ay = axis_fast(ly, myf, myi), az = axis_fast(lz, mzf, mzi);
-            float w[8];
+            float w[8], val[8];
             tri_weights(ax, ay, az, w);
-            float r;
-            {
-                const float *g = ib + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1));
-                const float val[8] = {__ldg(g), __ldg(g + 1), __ldg(g + GY), __ldg(g + GY + 1),
-                                      __ldg(g + GX), __ldg(g + GX + 1), __ldg(g + GX + GY), __ldg(g + GX + GY + 1)};
-                r = tri_accumulate(w, val);
-            }
+            gather8(ib + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1)), GY, GX, 1u, val);
+            float r = tri_accumulate(w, val);
             if (has_fill && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) r = fill;
             outb[vox0 + i * XS] = r;
         }
@@ -529,9 +523,9 @@ int launch_warp_brick(const float *img, const float *field, float *out, int B, i
     if (!tma_source_ok(img, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
     static const int cfg = getenv("DFM_WARP_CFG") ? atoi(getenv("DFM_WARP_CFG")) : 0;
     switch (cfg) {
-        case 1: return launch_warp_brick_t<8, 16, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 1: return launch_warp_brick_t<4, 10, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 2: return launch_warp_brick_t<8, 16, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 3: return launch_warp_brick_t<4, 10, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 3: return launch_warp_brick_t<4, 10, 18, 72>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 4: return launch_warp_brick_t<8, 14, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
     }

@@ -131,7 +131,8 @@ constexpr int WARP_ROWS = 4;
 static int launch_linear(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi,
                          int Zi, int X, int Y, int Z, int has_fill, float fill, unsigned flags,
                          cudaStream_t st) {
-    const uint32_t plane = (uint32_t)((Y + WARP_ROWS - 1) / WARP_ROWS) * Z;
+    const int rows = WARP_ROWS;
+    const uint32_t plane = (uint32_t)((Y + rows - 1) / rows) * Z;
     dim3 grid((plane + 255) / 256, X, B), block(256);
     FastDiv fd = make_fastdiv(Z);
     const bool fcl = flags & DFM_FIELD_IN_CL, icl = flags & DFM_IMG_CL;
