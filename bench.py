@@ -269,7 +269,7 @@ def run_own(args):
         kernels = {
             'ss_step(k_ss_brick)': {'launches_per_step': INT_STEPS, 'ms_per_launch': ss_ms / INT_STEPS,
                                     'algorithmic_bytes_per_launch': B * BYTES_SS_STEP, 'in_timed_region': True},
-            'rescale_x2(k_resize3_smem)': {'launches_per_step': 1, 'ms_per_launch': rs_ms,
+            'rescale_x2(k_upsample3_march)': {'launches_per_step': 1, 'ms_per_launch': rs_ms,
                                            'algorithmic_bytes_per_launch': B * BYTES_RESCALE, 'in_timed_region': True},
             'warp_linear(k_warp_brick)': {'launches_per_step': 1, 'ms_per_launch': wp_ms,
                                           'algorithmic_bytes_per_launch': B * BYTES_WARP, 'in_timed_region': True},
@@ -320,7 +320,7 @@ def run_own(args):
 # `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
 TRAFFIC_NCU_PER_PAIR = {
     'ss_step(k_ss_brick)': (59.004e6 + 22.844e6) / 8,
-    'rescale_x2(k_resize3_smem)': (59.011e6 + 414.804e6) / 8,
+    'rescale_x2(k_upsample3_march)': (59.011e6 + 414.804e6) / 8,
     'warp_linear(k_warp_brick)': (629.045e6 + 143.886e6) / 8,
 }
 
