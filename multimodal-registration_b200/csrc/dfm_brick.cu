@@ -98,10 +98,10 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
         if (i < nx) {
-            const uint32_t vox = vox0 + i * XS;
-            v[0][i] = __ldg(ownb + vox);
-            v[1][i] = __ldg(ownb + N + vox);
-            v[2][i] = __ldg(ownb + 2 * (size_t)N + vox);
+            const float *pv = ownb + vox0 + i * XS;
+            v[0][i] = __ldg(pv);
+            v[1][i] = __ldg(pv + N);
+            v[2][i] = __ldg(pv + 2 * (size_t)N);
         } else {
             v[0][i] = v[1][i] = v[2][i] = 0.f;
         }
@@ -133,43 +133,34 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     // lower-corner offset in the brick = i1x*PX + i1y*PY + i1z + cbase
     const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
     if (fits) {
-        // two voxels (x planes i, i+1) at a time: the packed FP32x2 pipe does both accumulations
-#pragma unroll
-        for (int i = 0; i < TX; i += 2) {
-            if (i >= nx) break;
-            const bool hasB = i + 1 < nx;             // odd tail: voxel B duplicates voxel A
-            const float a0 = v[0][i], a1 = v[1][i], a2 = v[2][i];
-            const float b0 = hasB ? v[0][i + 1] : a0, b1 = hasB ? v[1][i + 1] : a1, b2 = hasB ? v[2][i + 1] : a2;
-            const float fxa = fx0 + (float)i, fxb = hasB ? fx0 + (float)(i + 1) : fxa;
-            const AxisF ax = axis_fast(__fadd_rn(fxa, a0), mxf, mxi), bx = axis_fast(__fadd_rn(fxb, b0), mxf, mxi);
-            const AxisF ay = axis_fast(__fadd_rn(fy, a1), myf, myi), by = axis_fast(__fadd_rn(fy, b1), myf, myi);
-            const AxisF az = axis_fast(__fadd_rn(fz, a2), mzf, mzi), bz = axis_fast(__fadd_rn(fz, b2), mzf, mzi);
-            float wA[8], wB[8];
-            tri_weights_pair(ax, ay, az, bx, by, bz, wA, wB);
-            const float *qa = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
-            const float *qb = brick + (bx.i1 * PX + by.i1 * PY + bz.i1 + cbase);
-            float ra[3], rb[3];
+        float *o0 = outb + vox0, *o1 = o0 + N, *o2 = o1 + N;
+        auto voxel = [&](int i) {
+            const float v0 = v[0][i], v1 = v[1][i], v2 = v[2][i];
+            const AxisF ax = axis_fast(__fadd_rn(fx0 + (float)i, v0), mxf, mxi);
+            const AxisF ay = axis_fast(__fadd_rn(fy, v1), myf, myi);
+            const AxisF az = axis_fast(__fadd_rn(fz, v2), mzf, mzi);
+            float w[8];
+            tri_weights(ax, ay, az, w);
+            const float *q = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
+            float a[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float va[8] = {qa[c * CS], qa[c * CS + 1], qa[c * CS + PY], qa[c * CS + PY + 1],
-                                     qa[c * CS + PX], qa[c * CS + PX + 1], qa[c * CS + PX + PY], qa[c * CS + PX + PY + 1]};
-                const float vb[8] = {qb[c * CS], qb[c * CS + 1], qb[c * CS + PY], qb[c * CS + PY + 1],
-                                     qb[c * CS + PX], qb[c * CS + PX + 1], qb[c * CS + PX + PY], qb[c * CS + PX + PY + 1]};
-                tri_accumulate_pair(wA, wB, va, vb, ra[c], rb[c]);
+                const float val[8] = {q[c * CS], q[c * CS + 1], q[c * CS + PY], q[c * CS + PY + 1],
+                                      q[c * CS + PX], q[c * CS + PX + 1], q[c * CS + PX + PY], q[c * CS + PX + PY + 1]};
+                a[c] = tri_accumulate(w, val);
             }
-            if (SCALED) {
+            if (SCALED) { a[0] = __fmul_rn(scale, a[0]); a[1] = __fmul_rn(scale, a[1]); a[2] = __fmul_rn(scale, a[2]); }
+            o0[i * XS] = __fadd_rn(v0, a[0]);
+            o1[i * XS] = __fadd_rn(v1, a[1]);
+            o2[i * XS] = __fadd_rn(v2, a[2]);
+        };
+        if (nx == TX) {                               // interior thread: no predication in the loop
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { ra[c] = __fmul_rn(scale, ra[c]); rb[c] = __fmul_rn(scale, rb[c]); }
-            }
-            const uint32_t vox = vox0 + i * XS;
-            outb[vox] = __fadd_rn(a0, ra[0]);
-            outb[N + vox] = __fadd_rn(a1, ra[1]);
-            outb[2 * (size_t)N + vox] = __fadd_rn(a2, ra[2]);
-            if (hasB) {
-                outb[vox + XS] = __fadd_rn(b0, rb[0]);
-                outb[N + vox + XS] = __fadd_rn(b1, rb[1]);
-                outb[2 * (size_t)N + vox + XS] = __fadd_rn(b2, rb[2]);
-            }
+            for (int i = 0; i < TX; ++i) voxel(i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < TX; ++i)
+                if (i < nx) voxel(i);
         }
     } else {
         const float *srcb = src + (size_t)blockIdx.z * 3 * Ns;
