@@ -1,5 +1,7 @@
 // SpatialTransformer forward: out[b,c,p] = interp(img[b,c], p + field[b,:,p]).
 // Corner offsets/weights are built once per voxel and reused by every channel.
+#include <stdlib.h>
+
 #include "dfm_common.cuh"
 
 namespace dfm {
@@ -126,11 +128,120 @@ k_warp_nearest(const T *__restrict__ img, const float *__restrict__ field, T *__
     }
 }
 
+// one-channel linear warp, direct gathers, written for memory-level parallelism: a thread first
+// loads the field vectors of all its rows, then issues all 8*ROWS corner gathers, and only then
+// forms the weights and accumulates -- the loads of a thread are all in flight together, and the
+// small register footprint keeps many warps resident.  (Needs every image axis >= 2.)
+template <int ROWS, bool FIELD_CL>
+__global__ void __launch_bounds__(256, (ROWS == 1) ? 8 : 5)
+k_warp_linear1(const float *__restrict__ img, const float *__restrict__ field, float *__restrict__ out,
+               int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, float fill,
+               int abs_loc, FastDiv zdiv, uint32_t plane_items) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane_items) return;
+    const uint32_t yy = fast_div(p, zdiv);
+    const uint32_t z = p - yy * zdiv.d;
+    const uint32_t x = blockIdx.y;
+    const uint32_t N = (uint32_t)X * Y * Z, Ni = (uint32_t)Xi * Yi * Zi;
+    const float *fb = field + (size_t)blockIdx.z * 3 * N;
+    const float *ib = img + (size_t)blockIdx.z * Ni;
+    float *ob = out + (size_t)blockIdx.z * N;
+    const float fx = (float)x, fz = (float)z;
+    const uint32_t vox0 = (x * Y + yy * ROWS) * Z + z;
+    const int nr = min(ROWS, Y - (int)(yy * ROWS));
+    const uint32_t gy = (uint32_t)Zi, gx = (uint32_t)Yi * Zi;
+    const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    float l[ROWS][3];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        l[r][0] = l[r][1] = l[r][2] = 0.f;
+        if (r < nr) load_field1<FIELD_CL>(fb, N, vox0 + r * Z, l[r][0], l[r][1], l[r][2]);
+    }
+    float val[ROWS][8];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (!abs_loc) {
+            l[r][0] = __fadd_rn(fx, l[r][0]);
+            l[r][1] = __fadd_rn((float)(yy * ROWS + r), l[r][1]);
+            l[r][2] = __fadd_rn(fz, l[r][2]);
+        }
+        const uint32_t base = ((uint32_t)(axis_fast_i1(l[r][0], mxf, mxi) - 1) * Yi + (uint32_t)(axis_fast_i1(l[r][1], myf, myi) - 1)) * Zi +
+                              (uint32_t)(axis_fast_i1(l[r][2], mzf, mzi) - 1);
+        gather8(ib + base, gy, gx, 1u, val[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (r >= nr) break;
+        float w[8];
+        tri_weights(axis_fast(l[r][0], mxf, mxi), axis_fast(l[r][1], myf, myi), axis_fast(l[r][2], mzf, mzi), w);
+        float acc = tri_accumulate(w, val[r]);
+        if (has_fill && oob3(l[r][0], l[r][1], l[r][2], Xi, Yi, Zi)) acc = fill;
+        ob[vox0 + r * Z] = acc;
+    }
+}
+
+// one-channel nearest warp (label maps): latency-bound, so every thread first issues the field
+// loads of all its rows, then all gathers, then the stores (memory-level parallelism), and the
+// register budget allows 8 CTAs per SM
+template <typename T, int ROWS, bool FIELD_CL>
+__global__ void __launch_bounds__(256, 8)
+k_warp_nearest1(const T *__restrict__ img, const float *__restrict__ field, T *__restrict__ out,
+                int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, T fill,
+                int abs_loc, FastDiv zdiv, uint32_t plane_items) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane_items) return;
+    const uint32_t yy = fast_div(p, zdiv);
+    const uint32_t z = p - yy * zdiv.d;
+    const uint32_t x = blockIdx.y;
+    const uint32_t N = (uint32_t)X * Y * Z, Ni = (uint32_t)Xi * Yi * Zi;
+    const float *fb = field + (size_t)blockIdx.z * 3 * N;
+    const T *ib = img + (size_t)blockIdx.z * Ni;
+    T *ob = out + (size_t)blockIdx.z * N;
+    const float fx = (float)x, fz = (float)z;
+    const uint32_t vox0 = (x * Y + yy * ROWS) * Z + z;
+    const int nr = min(ROWS, Y - (int)(yy * ROWS));
+    float u[ROWS][3];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        u[r][0] = u[r][1] = u[r][2] = 0.f;
+        if (r < nr) load_field1<FIELD_CL>(fb, N, vox0 + r * Z, u[r][0], u[r][1], u[r][2]);
+    }
+    T val[ROWS];
+    bool oob[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const float lx = abs_loc ? u[r][0] : __fadd_rn(fx, u[r][0]);
+        const float ly = abs_loc ? u[r][1] : __fadd_rn((float)(yy * ROWS + r), u[r][1]);
+        const float lz = abs_loc ? u[r][2] : __fadd_rn(fz, u[r][2]);
+        const uint32_t off = ((uint32_t)axis_nearest(lx, Xi - 1) * Yi + axis_nearest(ly, Yi - 1)) * Zi + axis_nearest(lz, Zi - 1);
+        oob[r] = has_fill && oob3(lx, ly, lz, Xi, Yi, Zi);
+        val[r] = (r < nr) ? ib[off] : fill;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+        if (r < nr) ob[vox0 + r * Z] = oob[r] ? fill : val[r];
+}
+
 constexpr int WARP_ROWS = 4;
 
 static int launch_linear(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi,
                          int Zi, int X, int Y, int Z, int has_fill, float fill, unsigned flags,
                          cudaStream_t st) {
+    if (C == 1 && Xi >= 2 && Yi >= 2 && Zi >= 2) {
+        static const int r1 = getenv("DFM_WARP_ROWS1") ? 1 : 0;      // tuning aid
+        const int R = r1 ? 1 : 2;
+        const uint32_t pl = (uint32_t)((Y + R - 1) / R) * Z;
+        dim3 g((pl + 255) / 256, X, B), b(256);
+        const FastDiv fz_ = make_fastdiv(Z);
+        const int al = (flags & DFM_LOC_ABSOLUTE) ? 1 : 0;
+        const bool fc = flags & DFM_FIELD_IN_CL;
+#define DFM_G1(RR, F) k_warp_linear1<RR, F><<<g, b, 0, st>>>(img, field, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, al, fz_, pl)
+        if (R == 1) { if (fc) DFM_G1(1, true); else DFM_G1(1, false); }
+        else        { if (fc) DFM_G1(2, true); else DFM_G1(2, false); }
+#undef DFM_G1
+        return check_launch("dfm_warp_fwd(linear, C=1 direct)");
+    }
     const int rows = WARP_ROWS;
     const uint32_t plane = (uint32_t)((Y + rows - 1) / rows) * Z;
     dim3 grid((plane + 255) / 256, X, B), block(256);
@@ -156,6 +267,11 @@ static int launch_nearest(const void *img, const float *field, void *out, int B,
     const bool fcl = flags & DFM_FIELD_IN_CL, icl = flags & DFM_IMG_CL;
     const int abs_loc = (flags & DFM_LOC_ABSOLUTE) ? 1 : 0;
     const T fill = (T)fill_bits;
+    if (C == 1) {
+        if (fcl) k_warp_nearest1<T, WARP_ROWS, true><<<grid, block, 0, st>>>((const T *)img, field, (T *)out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, abs_loc, fd, plane);
+        else k_warp_nearest1<T, WARP_ROWS, false><<<grid, block, 0, st>>>((const T *)img, field, (T *)out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, abs_loc, fd, plane);
+        return check_launch("dfm_warp_fwd(nearest, C=1)");
+    }
 #define DFM_GO(F, I) k_warp_nearest<T, WARP_ROWS, F, I><<<grid, block, 0, st>>>( \
         (const T *)img, field, (T *)out, C, Xi, Yi, Zi, X, Y, Z, has_fill, fill, abs_loc, fd, plane)
     if (fcl) { if (icl) DFM_GO(true, true); else DFM_GO(true, false); }
