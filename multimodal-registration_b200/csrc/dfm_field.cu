@@ -7,6 +7,8 @@
 //    so every gather instruction touches 1-2 lines and the ROWS chains are independent (ILP).
 //  * k_ss_brick (dfm_brick.cu) -- planar linear path: the bounding box of the tile's sample
 //    locations is staged in shared memory by one TMA box load; see there.
+#include <stdlib.h>
+
 #include "dfm_common.cuh"
 
 namespace dfm {
@@ -86,6 +88,58 @@ k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, f
     }
 }
 
+// planar linear variant written for memory-level parallelism (see k_warp_linear1): all 24 corner
+// gathers of a voxel are issued before the first use, at a register budget that keeps 5 CTAs/SM.
+template <bool SCALED, bool OUT_CL>
+__global__ void __launch_bounds__(256, 5)
+k_field_warp_add1(const float *__restrict__ src, const float *__restrict__ own, float *__restrict__ out,
+                  int Xs, int Ys, int Zs, int X, int Y, int Z, float scale, FastDiv zdiv, uint32_t plane_items) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= plane_items) return;
+    const uint32_t y = fast_div(p, zdiv);
+    const uint32_t z = p - y * zdiv.d;
+    const uint32_t x = blockIdx.y;
+    const uint32_t N = (uint32_t)X * Y * Z, Ns = (uint32_t)Xs * Ys * Zs;
+    const float *ownb = own + (size_t)blockIdx.z * 3 * N;
+    const float *srcb = src + (size_t)blockIdx.z * 3 * Ns;
+    float *outb = out + (size_t)blockIdx.z * 3 * N;
+    const uint32_t vox = (x * Y + y) * Z + z;
+    const int mxi = Xs - 1, myi = Ys - 1, mzi = Zs - 1;
+    float v0 = __ldg(ownb + vox), v1 = __ldg(ownb + N + vox), v2 = __ldg(ownb + 2 * (size_t)N + vox);
+    if (SCALED) { v0 = __fmul_rn(scale, v0); v1 = __fmul_rn(scale, v1); v2 = __fmul_rn(scale, v2); }
+    const float lx = __fadd_rn((float)x, v0), ly = __fadd_rn((float)y, v1), lz = __fadd_rn((float)z, v2);
+    const AxisF ax = axis_fast(lx, (float)mxi, mxi), ay = axis_fast(ly, (float)myi, myi), az = axis_fast(lz, (float)mzi, mzi);
+    const uint32_t gy = (uint32_t)Zs, gx = (uint32_t)Ys * Zs;
+    const float *g = srcb + (((uint32_t)(ax.i1 - 1) * Ys + (uint32_t)(ay.i1 - 1)) * Zs + (uint32_t)(az.i1 - 1));
+    float a[3][8];
+    gather8(g, gy, gx, 1u, a[0]);
+    gather8(g + Ns, gy, gx, 1u, a[1]);
+    gather8(g + 2 * (size_t)Ns, gy, gx, 1u, a[2]);
+    float w[8];
+    tri_weights(ax, ay, az, w);
+    float r0 = tri_accumulate(w, a[0]), r1 = tri_accumulate(w, a[1]), r2 = tri_accumulate(w, a[2]);
+    if (SCALED) { r0 = __fmul_rn(scale, r0); r1 = __fmul_rn(scale, r1); r2 = __fmul_rn(scale, r2); }
+    r0 = __fadd_rn(v0, r0); r1 = __fadd_rn(v1, r1); r2 = __fadd_rn(v2, r2);
+    if (OUT_CL) {
+        outb[(size_t)vox * 3] = r0; outb[(size_t)vox * 3 + 1] = r1; outb[(size_t)vox * 3 + 2] = r2;
+    } else {
+        outb[vox] = r0; outb[N + vox] = r1; outb[2 * (size_t)N + vox] = r2;
+    }
+}
+
+static int launch_fwa1(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X, int Y,
+                       int Z, float scale, unsigned flags, cudaStream_t st) {
+    const uint32_t plane = (uint32_t)Y * Z;
+    dim3 grid((plane + 255) / 256, X, B), block(256);
+    FastDiv fd = make_fastdiv(Z);
+    const bool ocl = flags & DFM_FIELD_OUT_CL;
+#define DFM_GO(S, O) k_field_warp_add1<S, O><<<grid, block, 0, st>>>(src, own, out, Xs, Ys, Zs, X, Y, Z, scale, fd, plane)
+    if (scale == 1.f) { if (ocl) DFM_GO(false, true); else DFM_GO(false, false); }
+    else              { if (ocl) DFM_GO(true, true); else DFM_GO(true, false); }
+#undef DFM_GO
+    return check_launch("dfm_field_warp_add(direct, mlp)");
+}
+
 template <int INTERP>
 static int launch_fwa(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs,
                       int X, int Y, int Z, float scale, unsigned flags, cudaStream_t st) {
@@ -132,6 +186,8 @@ extern "C" int dfm_field_warp_add(const float *src, const float *own, float *out
             rc = launch_ss_brick(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, /*large_box=*/0, st);
             if (rc != DFM_EUNSUPPORTED) return rc;
         }
+        if (!(flags & DFM_FIELD_IN_CL) && Xs >= 2 && Ys >= 2 && Zs >= 2)
+            return launch_fwa1(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, flags, st);
         return launch_fwa<DFM_LINEAR>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, flags, st);
     }
     return launch_fwa<DFM_NEAREST>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, flags, st);
@@ -148,10 +204,15 @@ extern "C" size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nst
 // deformation) get the larger brick
 static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, float scale, unsigned flags,
                    int steps_left, cudaStream_t st) {
+    static const bool prefer_direct = getenv("DFM_SS_DIRECT") != nullptr;      // tuning aid
+    if (prefer_direct && !(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
+        return launch_fwa1(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
     if (brick_eligible(vin, vin, vout, X, Y, Z, X, Y, Z, flags)) {
         int rc = launch_ss_brick(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, steps_left < 2 ? 1 : 0, st);
         if (rc != DFM_EUNSUPPORTED) return rc;
     }
+    if (!(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
+        return launch_fwa1(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
     return launch_fwa<DFM_LINEAR>(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
 }
 

@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Config 3 (BASELINE.json): the deformation hot path of one train_synthmorph.py step with
+config/config.json shapes, forward + backward, batch-sharded across ranks.
+
+Per item: two labels_to_image generators (VecInt(5) -> x2 rescale -> nearest
+warp of a label map, fill_value 0), the VxmDense tail (x0.5 rescale of the full-resolution flow ->
+VecInt(5) -> x2 rescale -> linear warp of the source image, C=1), and
+`pred = SpatialTransformer('linear')([one_hot(26), flow])`; backward: d pred / d flow (C=26), the x2
+rescale adjoint, 5 SS-step adjoints, the x0.5 rescale adjoint.  The U-Net, the losses and the optimizer
+are outside the hot path; the upstream gradient of `pred` is a random tensor, the gradient that reaches
+the flow convolution is all-reduced across ranks together with a 1 446 979-float stand-in for the
+U-Net gradient bucket (the reference's only collective, train_synthmorph.py:284-285).
+
+  python scripts/bench_train_tail.py [--items 2] [--steps 5]
+  python -m torch.distributed.run --nproc-per-node N scripts/bench_train_tail.py
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+
+import bench
+import multimodal_registration_b200 as mrb
+from multimodal_registration_b200 import ops, sharding
+
+CFG = json.load(open(os.path.join(ROOT, 'config', 'config.json')))
+FULL = tuple(CFG['in_shape'])
+HALF = tuple(d // CFG['int_res'] for d in FULL)
+C = CFG['num_labels']
+STEPS = CFG['int_steps']
+N_F = FULL[0] * FULL[1] * FULL[2]
+N_H = HALF[0] * HALF[1] * HALF[2]
+# algorithmic bytes per item, SURVEY.md section 8(d)
+FWD = 2 * (STEPS * 24 * N_H + 12 * N_H + 12 * N_F + 20 * N_F) + (12 * N_F + 12 * N_H) + STEPS * 24 * N_H + \
+    (12 * N_H + 12 * N_F) + 20 * N_F + (8 * C + 12) * N_F
+BWD = (8 * C + 24) * N_F + (12 * N_F + 12 * N_H) + STEPS * 36 * N_H + (12 * N_F + 12 * N_H)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--items', type=int, default=2, help='items per GPU per step')
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    args = ap.parse_args()
+    rank, world = sharding.env_rank_world()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.items
+    g = torch.Generator(device='cpu').manual_seed(100 + rank)
+
+    def smooth(shape_c, std):
+        c = torch.randn(B, 3, *shape_c, generator=g) * std
+        return torch.nn.functional.interpolate(c, size=HALF, mode='trilinear', align_corners=True).permute(0, 2, 3, 4, 1).contiguous().to(dev)
+
+    vel = [smooth((10, 10, 12), CFG['vel_std'] / 2), smooth((10, 10, 12), CFG['vel_std'] / 2)]   # U(0, vel_std) mean
+    labels = [torch.randint(0, C, (B, *FULL, 1), generator=g).float().to(dev) for _ in range(2)]
+    flow_full = torch.nn.functional.interpolate(torch.randn(B, 3, 20, 20, 24, generator=g) * 1.5, size=FULL, mode='trilinear',
+                                                align_corners=True).permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    image = torch.rand(B, *FULL, 1, generator=g).to(dev)
+    unet_grad = torch.zeros(1446979, device=dev)
+
+    def step():
+        # generators (no gradient)
+        with torch.no_grad():
+            maps = []
+            for k in range(2):
+                w = ops.rescale_dense_transform(ops.vecint(vel[k], STEPS), 2)
+                maps.append(ops.warp(labels[k], w, 'nearest', fill_value=0))
+            onehot = torch.nn.functional.one_hot(maps[0][..., 0].long(), C).float()      # channels-last, like the reference
+            onehot_p = ops.to_layout(onehot, 'planar')
+        flow = flow_full.detach().requires_grad_(True)            # what the flow convolution emits (full res)
+        svf = ops.rescale_dense_transform(flow, 0.5)
+        pos = ops.rescale_dense_transform(ops.vecint(svf, STEPS), 2)
+        with torch.no_grad():
+            y_source = ops.warp(image, pos.detach())
+        pred = ops.warp(onehot_p, pos)
+        gpred = torch.rand_like(pred)
+        pred.backward(gpred)
+        sharding.allreduce_mean_(unet_grad)                       # the step's only collective
+        return flow.grad, y_source
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, src = bench.measured_peak_gbs()
+        ms = float(ms.item())
+        gbs = world * B * (FWD + BWD) / (ms * 1e-3) / 1e9
+        print(json.dumps({'workload': 'train_synthmorph.py step, deformation hot path fwd+bwd (config/config.json shapes)',
+                          'n_gpus': world, 'items_per_gpu': B, 'ms_per_step': ms, 'items_per_s': world * B / (ms * 1e-3),
+                          'algorithmic_GB_per_item': (FWD + BWD) / 1e9, 'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak,
+                          'includes': 'one_hot + layout conversion of the 26-channel map (torch / dfm_cl_to_planar), 5.79 MB all-reduce',
+                          'scaling': 'weak'}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
