@@ -117,8 +117,20 @@ k_warp_mc_brick(const __grid_constant__ CUtensorMap tmap, const float *__restric
         for (int c = 0; c < min(C, NSLOT - 1); ++c) issue(c);
 
     const uint32_t GX = (uint32_t)Yi * Zi, GY = (uint32_t)Zi;
+    // backward: the upstream gradient of channel c + 1 is fetched while channel c is processed
+    float gcur[MT_X], gnext[MT_X];
+#pragma unroll
+    for (int i = 0; i < MT_X; ++i) {
+        gcur[i] = gnext[i] = 0.f;
+        if (BWD && i < nx && !dead[i]) gcur[i] = __ldg(gout + (size_t)vol0 * N + vox0 + i * XS);
+    }
     for (int c = 0; c < C; ++c) {
         const float *ic = img + ((size_t)vol0 + c) * Ni;
+        if (BWD && c + 1 < C) {
+#pragma unroll
+            for (int i = 0; i < MT_X; ++i)
+                if (i < nx && !dead[i]) gnext[i] = __ldg(gout + ((size_t)vol0 + c + 1) * N + vox0 + i * XS);
+        }
         const float *q = ring + (size_t)(c % NSLOT) * CS;
         if (fits) mbar_wait(&bar[c % NSLOT], (uint32_t)((c / NSLOT) & 1));
 #pragma unroll
@@ -132,15 +144,18 @@ k_warp_mc_brick(const __grid_constant__ CUtensorMap tmap, const float *__restric
             } else {
                 gather8(ic + (uint32_t)base[i], GY, GX, 1u, val);
             }
-            const size_t o = ((size_t)vol0 + c) * N + vox0 + i * XS;
             if (!BWD) {
                 const float r = tri_accumulate(w[i], val);
-                out[o] = dead[i] ? fill : r;
+                out[((size_t)vol0 + c) * N + vox0 + i * XS] = dead[i] ? fill : r;
             } else {
-                const float g = dead[i] ? 0.f : __ldg(gout + o);
+                const float g = gcur[i];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(g, val[k], acc[i][k]);
             }
+        }
+        if (BWD) {
+#pragma unroll
+            for (int i = 0; i < MT_X; ++i) gcur[i] = gnext[i];
         }
         if (fits) {
             __syncthreads();                          // slot (c % NSLOT) is free again
