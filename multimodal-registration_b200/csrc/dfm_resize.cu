@@ -383,11 +383,14 @@ static int launch_resize3_smem(const float *in, float *out, const float *cx, con
 // The per-axis tap tables (first output index, tap count, weights) are computed by the host from
 // the same coordinate tables the forward kernel uses (`_coords.adjoint_taps`).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// KZ = compile-time z tap count (row length of zw): the z taps of a row are loaded together
+// (memory-level parallelism); rows shorter than KZ are zero-padded by the host tables.
+template <int KZ>
+__global__ void __launch_bounds__(256)
 k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const int *__restrict__ xlo,
              const int *__restrict__ xcnt, const float *__restrict__ xw, int kx, const int *__restrict__ ylo,
              const int *__restrict__ ycnt, const float *__restrict__ yw, int ky, const int *__restrict__ zlo,
-             const int *__restrict__ zcnt, const float *__restrict__ zw, int kz, int Xi, int Yi, int Zi, int Xo,
+             const float *__restrict__ zw, int Xi, int Yi, int Zi, int Xo,
              int Yo, int Zo, float s, FastDiv zdiv, uint32_t plane_items) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plane_items) return;
@@ -398,15 +401,26 @@ k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const int 
     const size_t No = (size_t)Xo * Yo * Zo, Ni = (size_t)Xi * Yi * Zi;
     const float *gb = gout + (size_t)bc * No;
     const int x0 = __ldg(xlo + ix), nx = __ldg(xcnt + ix), y0 = __ldg(ylo + iy), ny = __ldg(ycnt + iy);
-    const int z0 = __ldg(zlo + iz), nz = __ldg(zcnt + iz);
+    const int z0 = __ldg(zlo + iz);
+    float wz[KZ];
+    int oz[KZ];
+#pragma unroll
+    for (int c = 0; c < KZ; ++c) {
+        wz[c] = __ldg(zw + iz * KZ + c);
+        oz[c] = min(z0 + c, Zo - 1);                 // padded taps have weight 0: any valid address
+    }
     float acc = 0.f;
     for (int a = 0; a < nx; ++a) {
         const float wx = __ldg(xw + ix * kx + a);
         float accy = 0.f;
         for (int b = 0; b < ny; ++b) {
-            const float *row = gb + ((size_t)(x0 + a) * Yo + (y0 + b)) * Zo + z0;
+            const float *row = gb + ((size_t)(x0 + a) * Yo + (y0 + b)) * Zo;
+            float v[KZ];
+#pragma unroll
+            for (int c = 0; c < KZ; ++c) v[c] = __ldg(row + oz[c]);
             float accz = 0.f;
-            for (int c = 0; c < nz; ++c) accz = fmaf(__ldg(zw + iz * kz + c), __ldg(row + c), accz);
+#pragma unroll
+            for (int c = 0; c < KZ; ++c) accz = fmaf(wz[c], v[c], accz);
             accy = fmaf(__ldg(yw + iy * ky + b), accz, accy);
         }
         acc = fmaf(wx, accy, acc);
@@ -459,9 +473,24 @@ extern "C" int dfm_resize_bwd(const float *gout, float *gin, const int *xlo, con
     if (B == 0) return DFM_OK;
     DFM_REQUIRE(gout && gin && xlo && xcnt && xw && ylo && ycnt && yw && zlo && zcnt && zw, DFM_EINVAL,
                 "dfm_resize_bwd: null pointer");
+    (void)zcnt;   // rows of zw are zero-padded to kz taps, so the z count is not needed on the device
     const uint32_t plane = (uint32_t)Yi * Zi;
-    dim3 grid((plane + 127) / 128, Xi, B * C), block(128);
-    k_resize_bwd<<<grid, block, 0, (cudaStream_t)stream>>>(gout, gin, xlo, xcnt, xw, kx, ylo, ycnt, yw, ky, zlo, zcnt, zw,
-                                                          kz, Xi, Yi, Zi, Xo, Yo, Zo, pre * post, make_fastdiv(Zi), plane);
+    dim3 grid((plane + 255) / 256, Xi, B * C), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const FastDiv fd = make_fastdiv(Zi);
+    const float sc = pre * post;
+#define DFM_GO(K) k_resize_bwd<K><<<grid, block, 0, st>>>(gout, gin, xlo, xcnt, xw, kx, ylo, ycnt, yw, ky, zlo, zw, Xi, Yi, Zi, Xo, Yo, Zo, sc, fd, plane)
+    switch (kz) {
+        case 1: DFM_GO(1); break;
+        case 2: DFM_GO(2); break;
+        case 3: DFM_GO(3); break;
+        case 4: DFM_GO(4); break;
+        case 5: DFM_GO(5); break;
+        case 6: DFM_GO(6); break;
+        case 7: DFM_GO(7); break;
+        case 8: DFM_GO(8); break;
+        default: return fail(DFM_EUNSUPPORTED, "dfm_resize_bwd: %d z taps per input sample (max 8: zoom factors up to ~4)", kz);
+    }
+#undef DFM_GO
     return check_launch("dfm_resize_bwd");
 }
