@@ -183,7 +183,8 @@ extern "C" int dfm_field_warp_add(const float *src, const float *own, float *out
     cudaStream_t st = (cudaStream_t)stream;
     if (interp == DFM_LINEAR) {
         if (brick_eligible(src, own, out, Xs, Ys, Zs, X, Y, Z, flags)) {
-            rc = launch_ss_brick(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, /*large_box=*/0, st);
+            // a stand-alone call (compose, a single SS step) sees full-size displacements: larger brick
+            rc = launch_ss_brick(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, /*large_box=*/1, st);
             if (rc != DFM_EUNSUPPORTED) return rc;
         }
         if (!(flags & DFM_FIELD_IN_CL) && Xs >= 2 && Ys >= 2 && Zs >= 2)

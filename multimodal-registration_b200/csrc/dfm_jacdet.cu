@@ -178,14 +178,14 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
                         const float dx = d4f(win[c][r][(K + 1) % 5], win[c][r][(K + 2) % 5], win[c][r][(K + 4) % 5], win[c][r][K]); \
                         const float dy = d4f(PL(cs, c, yy - 2, zz), PL(cs, c, yy - 1, zz), PL(cs, c, yy + 1, zz), PL(cs, c, yy + 2, zz)); \
                         const float dz = d4f(PL(cs, c, yy, zz - 2), PL(cs, c, yy, zz - 1), PL(cs, c, yy, zz + 1), PL(cs, c, yy, zz + 2)); \
-                        J[c][0] = (double)dx * (1.0 / 12.0);                                                          \
-                        J[c][1] = (double)dy * (1.0 / 12.0);                                                          \
-                        J[c][2] = (double)dz * (1.0 / 12.0);                                                          \
+                        J[c][0] = (double)dx;      /* 12 * du_c/dx: det(I + J) = det(12 I + 12 J) / 12^3 */           \
+                        J[c][1] = (double)dy;                                                                         \
+                        J[c][2] = (double)dz;                                                                         \
                     }                                                                                                 \
-                    J[0][0] += 1.0; J[1][1] += 1.0; J[2][2] += 1.0;                                                   \
-                    const double dval = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -                           \
-                                        J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +                           \
-                                        J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);                            \
+                    J[0][0] += 12.0; J[1][1] += 12.0; J[2][2] += 12.0;                                                \
+                    const double dval = (J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -                          \
+                                         J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +                          \
+                                         J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0])) * (1.0 / 1728.0);         \
                     if (det)                                                                                          \
                         det[(size_t)blockIdx.z * Xo * Yo * Zo + ((size_t)xo * Yo + (yo0 + warp + 8 * r)) * Zo + zo] = (Tout)dval; \
                     s += dval; s2 += dval * dval; nn += (dval < 0.0) ? 1.0 : 0.0;                                     \
