@@ -74,9 +74,31 @@ def empty(shape, layout, device, dtype=torch.float32):
     return storage.permute(_perm_to_logical(nd))
 
 
+class _ToLayout(torch.autograd.Function):
+    """A layout change is the identity on the logical tensor, so its gradient passes through."""
+
+    @staticmethod
+    def forward(ctx, t, layout):
+        return _to_layout_raw(t, layout)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 def to_layout(t, layout):
     """Return ``t`` (logical shape unchanged) in physical layout 'cl' or 'planar' using the
-    library's own transposition kernels; no-op if it already is."""
+    library's own transposition kernels; no-op if it already is.  Differentiable."""
+    cur = layout_of(t)
+    if cur == 'both' or cur == layout:
+        return t
+    if torch.is_grad_enabled() and t.requires_grad:
+        return _ToLayout.apply(t, layout)
+    return _to_layout_raw(t, layout)
+
+
+def _to_layout_raw(t, layout):
+    t = t.detach()
     cur = layout_of(t)
     if cur == 'both' or cur == layout:
         return t
