@@ -120,6 +120,20 @@ class VxmDense(torch.nn.Module):
         second = {'svf': svf, 'preintegrated': preint_flow}.get(self.reg_field, pos_flow)
         return [y_source, second]
 
+    def deform_graphed(self, inputs):
+        """``deform`` through a cached CUDA graph (one per input shape): single-volume inference is
+        launch-bound, a replay submits the whole tail in one call.  Device tensors in, static device
+        tensors out (valid until the next call with the same shapes)."""
+        source = _host.to_device(inputs[0], torch.float32, tag='source')
+        flow = _host.to_device(inputs[1], torch.float32, tag='flow')
+        key = (tuple(source.shape), tuple(flow.shape), ops.layout_of(source), ops.layout_of(flow))
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = ops.Graphed(lambda s, f: tuple(self.deform([s, f])), source, flow)
+        return list(g(source, flow))
+
     def forward(self, inputs):
         if self.flow_model is None:
             raise NotImplementedError(

@@ -282,6 +282,19 @@ def test_chunked_predict_equals_single_call():
     assert_linear_parity(w3, io.rescale_dense_transform(io.vec_int(half, 5), 2))
 
 
+def test_cuda_graph_replay_matches_eager():
+    rng = np.random.default_rng(73)
+    model = vxm.networks.VxmDense((16, 16, 32), int_steps=7, svf_resolution=2, int_resolution=2)
+    for trial in range(3):                                   # same shapes -> one capture, three replays
+        scan = rng.random((1, 16, 16, 32, 1)).astype(np.float32)
+        half = smooth_noise(rng, (1, 8, 8, 16, 3), 1.5, smooth=1)
+        eager = [host(t) if t.dim() == 5 else t for t in model.deform([dev(scan), dev(half)])]
+        y, pre = model.deform_graphed([dev(scan), dev(half)])
+        np.testing.assert_array_equal(host(y), eager[0])
+        np.testing.assert_array_equal(host(pre), half)
+    assert len(model._graphs) == 1
+
+
 def test_fused_rescale_warp_matches_unfused_bitwise():
     rng = np.random.default_rng(61)
     for shape, B in [((8, 12, 16), 2), ((20, 20, 48), 1), ((6, 5, 7), 1)]:
