@@ -181,6 +181,20 @@ int dfm_jacdet(const void *field, void *det, double *stats, void *partials,
                unsigned flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Sub-volume stitching  (3d_reg.py:214-259 get_def_field_from_subvol; duplicated in
+ * bids_registration.py:226-271 and bids_two_steps_registration.py:226-271)
+ *   tiles: T fields of shape (tx,ty,tz), channels-last [T][tx][ty][tz][3] (DFM_FIELD_IN_CL, what
+ *          model.predict returns) or planar [T][3][tx][ty][tz]; mins: DEVICE int [T][3], the
+ *          (x_min, y_min, z_min) of every tile in the volume; out: [X][Y][Z][3] (DFM_FIELD_OUT_CL)
+ *          or planar [3][X][Y][Z], fp32 or fp64 (out_f64).
+ *   out[p] = sum_t (w_t(p) / sum_t' w_t'(p)) * tile_t[p - min_t],  w = 1 - max(|x|,|y|,|z|)/(max+1)
+ *   on the tile-centred grid [-s/2, s/2); float64 arithmetic in tile order (bit-identical to the
+ *   reference); voxels no tile covers are 0.
+ * ------------------------------------------------------------------------------------- */
+int dfm_stitch_subvol(const float *tiles, const int *mins, void *out, int T, int tx, int ty, int tz,
+                      int X, int Y, int Z, int out_f64, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Layout conversion between the reference's channels-last tensors and planar tensors.
  *   cl [B][N][C]  <->  planar [B][C][N],  elem_size in {1, 2, 4, 8}.
  * ------------------------------------------------------------------------------------- */

@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 _PINNED = {}
+_BUSY = {}      # staging buffer key -> event of the last async copy that READ from it
 
 
 def _pinned(shape, dtype, tag):
@@ -16,9 +17,19 @@ def _pinned(shape, dtype, tag):
     if buf is None:
         if len(_PINNED) > 64:
             _PINNED.clear()
+            _BUSY.clear()
         buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         _PINNED[key] = buf
+    ev = _BUSY.get(key)
+    if ev is not None:
+        ev.synchronize()          # an earlier H2D copy may still be reading this buffer
     return buf
+
+
+def _mark_busy(shape, dtype, tag):
+    ev = torch.cuda.Event()
+    ev.record()
+    _BUSY[(tuple(shape), dtype, tag)] = ev
 
 
 def device():
@@ -47,7 +58,9 @@ def to_device(x, dtype=None, tag='in'):
     if not t.is_pinned():
         stage = _pinned(t.shape, t.dtype, tag)
         stage.copy_(t)
-        t = stage
+        out = stage.to(dev, non_blocking=True)
+        _mark_busy(t.shape, t.dtype, tag)   # the staging buffer must not be overwritten before this copy ran
+        return out
     return t.to(dev, non_blocking=True)
 
 

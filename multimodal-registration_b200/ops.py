@@ -454,6 +454,39 @@ def rescale_warp(img, coarse_field, factor, fill_value=None):
 
 
 # ---------------------------------------------------------------------------------------
+# sub-volume stitching
+# ---------------------------------------------------------------------------------------
+def stitch_subvolumes(model_in_shape, im_shape, lst_coords_subvol, lst_warp_subvol, out_dtype=torch.float64):
+    """``get_def_field_from_subvol`` of the reference scripts (3d_reg.py:214-259): pyramid-weighted
+    average of overlapping tile fields.  ``lst_warp_subvol``: T arrays/tensors ``[tx, ty, tz, 3]`` (or one
+    stacked ``[T, tx, ty, tz, 3]`` tensor); ``lst_coords_subvol``: T tuples (x_min, x_max, y_min, y_max,
+    z_min, z_max).  Returns the channels-last field ``[X, Y, Z, 3]`` on the device (float64 like the
+    reference by default)."""
+    from . import _host
+    tx, ty, tz = (int(d) for d in model_in_shape)
+    X, Y, Z = (int(d) for d in im_shape[:3])
+    if isinstance(lst_warp_subvol, torch.Tensor):
+        tiles = _host.to_device(lst_warp_subvol, torch.float32)
+    else:
+        tiles = torch.stack([_host.to_device(w, torch.float32) for w in lst_warp_subvol], 0)
+    T = tiles.shape[0]
+    if len(lst_coords_subvol) != T or tuple(tiles.shape[1:]) != (tx, ty, tz, 3):
+        raise ValueError('stitch_subvolumes: %d coordinate tuples for tiles of shape %s (expected [T, %d, %d, %d, 3])'
+                         % (len(lst_coords_subvol), tuple(tiles.shape), tx, ty, tz))
+    for c in lst_coords_subvol:
+        if c[1] - c[0] != tx or c[3] - c[2] != ty or c[5] - c[4] != tz or c[0] < 0 or c[2] < 0 or c[4] < 0 \
+                or c[1] > X or c[3] > Y or c[5] > Z:
+            raise ValueError('stitch_subvolumes: tile %s does not match the tile shape or leaves the volume' % (c,))
+    tiles, in_cl = _field_layout(tiles, 'tiles')
+    mins = torch.tensor([[c[0], c[2], c[4]] for c in lst_coords_subvol], dtype=torch.int32).to(tiles.device)
+    out = torch.empty((X, Y, Z, 3), device=tiles.device, dtype=out_dtype)
+    flags = (_lib.FIELD_IN_CL if in_cl else 0) | _lib.FIELD_OUT_CL
+    _lib.call('dfm_stitch_subvol', _ptr(tiles), _ptr(mins), _ptr(out), T, tx, ty, tz, X, Y, Z,
+              int(out_dtype == torch.float64), flags, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # CUDA graphs
 # ---------------------------------------------------------------------------------------
 class Graphed:

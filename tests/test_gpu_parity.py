@@ -282,6 +282,33 @@ def test_chunked_predict_equals_single_call():
     assert_linear_parity(w3, io.rescale_dense_transform(io.vec_int(half, 5), 2))
 
 
+def test_stitch_subvolumes_against_reference_goldens():
+    import importlib.util
+    from oracle import stitch_oracle as so
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location('make_stitch_golden', os.path.join(here, 'golden', 'make_stitch_golden.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    paths = sorted(glob.glob(os.path.join(here, 'golden', 'stitch_*.npz')))
+    assert len(paths) >= 3
+    for path in paths:
+        g = np.load(path)
+        coords = [tuple(int(v) for v in c) for c in g['coords']]
+        warps = gen.make_warps(int(g['seed']), g['in_shape'], len(coords))
+        got = ops.stitch_subvolumes(tuple(g['in_shape']), tuple(g['vol_shape']), coords, warps)
+        assert got.dtype == torch.float64
+        np.testing.assert_array_equal(got.cpu().numpy(), g['out'])          # bit-identical to the reference
+        got32 = ops.stitch_subvolumes(tuple(g['in_shape']), tuple(g['vol_shape']), coords,
+                                      ops.to_layout(torch.from_numpy(np.stack(warps)).cuda(), 'planar'), out_dtype=torch.float32)
+        np.testing.assert_allclose(got32.cpu().numpy(), g['out'], rtol=1e-6, atol=1e-6)
+    # uncovered voxels stay zero
+    f = np.random.default_rng(0).standard_normal((8, 8, 8, 3)).astype(np.float32)
+    out = ops.stitch_subvolumes((8, 8, 8), (12, 8, 8), [(0, 8, 0, 8, 0, 8)], [f]).cpu().numpy()
+    np.testing.assert_array_equal(out, so.get_def_field_from_subvol((8, 8, 8), (12, 8, 8), [(0, 8, 0, 8, 0, 8)], [f]))
+    with pytest.raises(ValueError):
+        ops.stitch_subvolumes((8, 8, 8), (12, 8, 8), [(6, 14, 0, 8, 0, 8)], [f])
+
+
 def test_cuda_graph_replay_matches_eager():
     rng = np.random.default_rng(73)
     model = vxm.networks.VxmDense((16, 16, 32), int_steps=7, svf_resolution=2, int_resolution=2)
