@@ -104,8 +104,8 @@ k_jacdet_finalize(const double *__restrict__ partials, double *__restrict__ stat
 // column, the y and z stencils from the shared plane.  The four-point stencil is evaluated in
 // fp32 in difference form  ((u[-2] - u[+2]) + 8 (u[+1] - u[-1]))  -- differences of neighbouring
 // samples, so the fp32 rounding is relative to the local variation of the field (~1e-7 for
-// registration fields) -- then converted once per derivative and the determinant, the fold test
-// and the moments are done in fp64.  (The all-fp64 kernel above needs 36 fp32->fp64 conversions
+// registration fields); the three 2x2 minors are fp32 (one fused rounding each), the expansion along
+// the first row, the fold test and the moments are fp64.  (The all-fp64 kernel above needs 36 fp32->fp64 conversions
 // per voxel, which run at 1/8 rate; it is kept for fp64 inputs and channels-last fields.)
 // ---------------------------------------------------------------------------------------
 constexpr int JT_X = 32, JT_Y = 16, JT_Z = 32, JP_Y = JT_Y + 4, JP_Z = JT_Z + 4, J_SLOTS = 5;
@@ -173,19 +173,19 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
             _Pragma("unroll") for (int r = 0; r < 2; ++r) {                                                           \
                 if (okz && (r ? oky1 : oky0)) {                                                                       \
                     const int yy = warp + 8 * r + 2, zz = lane + 2;                                                   \
-                    double J[3][3];                                                                                   \
+                    float J[3][3];         /* 12 * (I + grad u): det(I + J) = det(12 I + 12 J) / 12^3 */                \
                     _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                   \
-                        const float dx = d4f(win[c][r][(K + 1) % 5], win[c][r][(K + 2) % 5], win[c][r][(K + 4) % 5], win[c][r][K]); \
-                        const float dy = d4f(PL(cs, c, yy - 2, zz), PL(cs, c, yy - 1, zz), PL(cs, c, yy + 1, zz), PL(cs, c, yy + 2, zz)); \
-                        const float dz = d4f(PL(cs, c, yy, zz - 2), PL(cs, c, yy, zz - 1), PL(cs, c, yy, zz + 1), PL(cs, c, yy, zz + 2)); \
-                        J[c][0] = (double)dx;      /* 12 * du_c/dx: det(I + J) = det(12 I + 12 J) / 12^3 */           \
-                        J[c][1] = (double)dy;                                                                         \
-                        J[c][2] = (double)dz;                                                                         \
+                        J[c][0] = d4f(win[c][r][(K + 1) % 5], win[c][r][(K + 2) % 5], win[c][r][(K + 4) % 5], win[c][r][K]); \
+                        J[c][1] = d4f(PL(cs, c, yy - 2, zz), PL(cs, c, yy - 1, zz), PL(cs, c, yy + 1, zz), PL(cs, c, yy + 2, zz)); \
+                        J[c][2] = d4f(PL(cs, c, yy, zz - 2), PL(cs, c, yy, zz - 1), PL(cs, c, yy, zz + 1), PL(cs, c, yy, zz + 2)); \
                     }                                                                                                 \
-                    J[0][0] += 12.0; J[1][1] += 12.0; J[2][2] += 12.0;                                                \
-                    const double dval = (J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) -                          \
-                                         J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +                          \
-                                         J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0])) * (1.0 / 1728.0);         \
+                    J[0][0] += 12.f; J[1][1] += 12.f; J[2][2] += 12.f;                                                \
+                    /* 2x2 minors in fp32 with one fused rounding each, combined and scaled in fp64 */                \
+                    const float m0 = fmaf(J[1][1], J[2][2], -J[1][2] * J[2][1]);                                      \
+                    const float m1 = fmaf(J[1][0], J[2][2], -J[1][2] * J[2][0]);                                      \
+                    const float m2 = fmaf(J[1][0], J[2][1], -J[1][1] * J[2][0]);                                      \
+                    const double dval = ((double)J[0][0] * (double)m0 - (double)J[0][1] * (double)m1 +                \
+                                         (double)J[0][2] * (double)m2) * (1.0 / 1728.0);                              \
                     if (det)                                                                                          \
                         det[(size_t)blockIdx.z * Xo * Yo * Zo + ((size_t)xo * Yo + (yo0 + warp + 8 * r)) * Zo + zo] = (Tout)dval; \
                     s += dval; s2 += dval * dval; nn += (dval < 0.0) ? 1.0 : 0.0;                                     \
