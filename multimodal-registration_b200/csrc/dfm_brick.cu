@@ -31,30 +31,28 @@ namespace dfm {
 
 constexpr int TY = 8, TZ = 32;
 
-// block-wide bounding box of the corner indices: lower corner i1 - 1, upper corner i1
+// block-wide bounding box of the corner indices: lower corner i1 - 1, upper corner i1.
+// i1 is monotone in the clipped location, so each thread tracks min/max of its CLIPPED locations in
+// float and converts only the six extremes; every lane then issues the shared-memory atomics (the
+// compiler aggregates them per warp with CREDUX + one elected ATOMS -- doing the warp reduction by
+// hand as well makes it reduce twice).
 struct BoxReduce {
-    int mn[3], mx[3];
-    __device__ __forceinline__ void init() {
-        mn[0] = mn[1] = mn[2] = INT_MAX;
-        mx[0] = mx[1] = mx[2] = INT_MIN;
+    float mn[3], mx[3];
+    __device__ __forceinline__ void first(float cx, float cy, float cz) {
+        mn[0] = mx[0] = cx; mn[1] = mx[1] = cy; mn[2] = mx[2] = cz;
     }
-    __device__ __forceinline__ void add(int ix, int iy, int iz) {
-        mn[0] = min(mn[0], ix); mn[1] = min(mn[1], iy); mn[2] = min(mn[2], iz);
-        mx[0] = max(mx[0], ix); mx[1] = max(mx[1], iy); mx[2] = max(mx[2], iz);
+    __device__ __forceinline__ void add(float cx, float cy, float cz) {
+        mn[0] = fminf(mn[0], cx); mn[1] = fminf(mn[1], cy); mn[2] = fminf(mn[2], cz);
+        mx[0] = fmaxf(mx[0], cx); mx[1] = fmaxf(mx[1], cy); mx[2] = fmaxf(mx[2], cz);
     }
-    // s_min/s_max: shared int[3] initialised to INT_MAX / INT_MIN before the preceding barrier
-    __device__ __forceinline__ void commit(int *s_min, int *s_max, int lane) {
+    // s_min/s_max: shared int[3] initialised to INT_MAX / INT_MIN before the preceding barrier;
+    // they receive min(i1) and max(i1)
+    __device__ __forceinline__ void commit(int *s_min, int *s_max, int mxi, int myi, int mzi) {
+        const int mi[3] = {mxi, myi, mzi};
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            mn[d] = __reduce_min_sync(0xffffffffu, mn[d]);
-            mx[d] = __reduce_max_sync(0xffffffffu, mx[d]);
-        }
-        if (lane == 0 && mn[0] != INT_MAX) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                atomicMin(&s_min[d], mn[d] - 1);       // lower corner index
-                atomicMax(&s_max[d], mx[d]);           // upper corner index
-            }
+            atomicMin(&s_min[d], axis_clipped_i1(mn[d], mi[d]));
+            atomicMax(&s_max[d], axis_clipped_i1(mx[d], mi[d]));
         }
     }
 };
@@ -66,7 +64,7 @@ template <int TX, int BX, int BY, int BZ, bool SCALED>
 __global__ void __launch_bounds__(256)
 k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src,
            const float *__restrict__ own, float *__restrict__ out, int Xs, int Ys, int Zs, int X, int Y,
-           int Z, float scale, int nzt) {
+           int Z, float scale, FastDiv nzt, const float *__restrict__ bound, float bscale) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *brick = reinterpret_cast<float *>(smem_raw);   // [3][BX][BY][BZ]
     __shared__ __align__(8) uint64_t bar;
@@ -74,22 +72,41 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     constexpr int PX = BY * BZ, PY = BZ, CS = BX * BY * BZ;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
+    const int yt = (int)fast_div(blockIdx.x, nzt), zt = (int)blockIdx.x - yt * (int)nzt.d;
     const int z = zt * TZ + lane, y = yt * TY + warp, x0 = blockIdx.y * TX;
     const bool ok_yz = (z < Z) && (y < Y);
+    // threads past the volume edge shadow the nearest voxel inside (loads and the bounding box run
+    // unpredicated; only their stores are masked)
+    const int zc = min(z, Z - 1), yc = min(y, Y - 1);
+    const int nx = min(TX, X - x0);                       // CTA-uniform, >= 1
     const uint32_t N = (uint32_t)X * Y * Z, Ns = (uint32_t)Xs * Ys * Zs;
     const float *ownb = own + (size_t)blockIdx.z * 3 * N;
     float *outb = out + (size_t)blockIdx.z * 3 * N;
     const int mxi = Xs - 1, myi = Ys - 1, mzi = Zs - 1;
     const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
-    const float fy = (float)y, fz = (float)z, fx0 = (float)x0;
-    const uint32_t vox0 = ((uint32_t)x0 * Y + y) * Z + z, XS = (uint32_t)Y * Z;
-    const int nx = ok_yz ? min(TX, X - x0) : 0;          // voxels this thread owns
+    const float fy = (float)yc, fz = (float)zc, fx0 = (float)x0;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + yc) * Z + zc, XS = (uint32_t)Y * Z;
+    const bool same_grid = (Xs == X) && (Ys == Y) && (Zs == Z);
+
+    // Static halo: when the caller can bound the displacements of this batch item (|v| < HS voxels --
+    // the early scaling-and-squaring steps; `bound[b] * bscale` is that bound), the corners of the
+    // tile lie inside [tile - HS, tile + HS], so the brick is requested before the own vectors are
+    // even loaded and the bounding-box reduction (and its barrier) disappears.
+    constexpr int HS_XY = (BX - TX) / 2 < (BY - TY) / 2 ? (BX - TX) / 2 : (BY - TY) / 2;
+    constexpr int HS_Z = BZ - TZ - 5 < 4 ? BZ - TZ - 5 : 4;      // origin z0 - 4 (16-byte aligned), upper corner z0 + 31 + HS + 1
+    constexpr int HS = HS_XY < HS_Z ? HS_XY : HS_Z;
+    const bool stat = HS >= 1 && bound != nullptr && same_grid &&
+                      __ldg(bound + blockIdx.z) * bscale < (float)HS * 0.999f;       // CTA-uniform
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
-        s_min[0] = s_min[1] = s_min[2] = INT_MAX;
-        s_max[0] = s_max[1] = s_max[2] = INT_MIN;
+        if (stat) {
+            mbar_expect_tx(&bar, 3u * CS * sizeof(float));
+            tma_load_4d(brick, &tmap, &bar, zt * TZ - 4, yt * TY - HS, x0 - HS, (int)blockIdx.z * 3);
+        } else {
+            s_min[0] = s_min[1] = s_min[2] = INT_MAX;
+            s_max[0] = s_max[1] = s_max[2] = INT_MIN;
+        }
     }
     __syncthreads();
 
@@ -97,35 +114,42 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     float v[3][TX];
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
-        if (i < nx) {
-            const float *pv = ownb + vox0 + i * XS;
-            v[0][i] = __ldg(pv);
-            v[1][i] = __ldg(pv + N);
-            v[2][i] = __ldg(pv + 2 * (size_t)N);
-        } else {
-            v[0][i] = v[1][i] = v[2][i] = 0.f;
-        }
+        const int ic = min(i, nx - 1);
+        const float *pv = ownb + vox0 + ic * XS;
+        v[0][i] = __ldg(pv);
+        v[1][i] = __ldg(pv + N);
+        v[2][i] = __ldg(pv + 2 * (size_t)N);
     }
-    BoxReduce box;
-    box.init();
+    int ox, oy, oz;
+    bool fits;
+    if (stat) {
 #pragma unroll
-    for (int i = 0; i < TX; ++i) {
-        if (SCALED) {
-            v[0][i] = __fmul_rn(scale, v[0][i]); v[1][i] = __fmul_rn(scale, v[1][i]); v[2][i] = __fmul_rn(scale, v[2][i]);
+        for (int i = 0; i < TX; ++i)
+            if (SCALED) {
+                v[0][i] = __fmul_rn(scale, v[0][i]); v[1][i] = __fmul_rn(scale, v[1][i]); v[2][i] = __fmul_rn(scale, v[2][i]);
+            }
+        ox = x0 - HS; oy = yt * TY - HS; oz = zt * TZ - 4;             // brick origin = lower corner index
+        fits = true;
+    } else {
+        BoxReduce box;
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            if (SCALED) {
+                v[0][i] = __fmul_rn(scale, v[0][i]); v[1][i] = __fmul_rn(scale, v[1][i]); v[2][i] = __fmul_rn(scale, v[2][i]);
+            }
+            const float fx = fx0 + (float)min(i, nx - 1);
+            const float cx = axis_clip(__fadd_rn(fx, v[0][i]), mxf), cy = axis_clip(__fadd_rn(fy, v[1][i]), myf),
+                        cz = axis_clip(__fadd_rn(fz, v[2][i]), mzf);
+            if (i == 0) box.first(cx, cy, cz); else box.add(cx, cy, cz);
         }
-        if (i < nx)
-            box.add(axis_fast_i1(__fadd_rn(fx0 + (float)i, v[0][i]), mxf, mxi),
-                    axis_fast_i1(__fadd_rn(fy, v[1][i]), myf, myi), axis_fast_i1(__fadd_rn(fz, v[2][i]), mzf, mzi));
-    }
-    box.commit(s_min, s_max, lane);
-    __syncthreads();
-    const int ox = s_min[0], oy = s_min[1], oz = s_min[2] & ~3;
-    if (ox == INT_MAX) return;                        // tile entirely outside the volume (uniform)
-    const bool fits = (s_max[0] - ox < BX) && (s_max[1] - oy < BY) && (s_max[2] - oz < BZ);
-
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, 3u * CS * sizeof(float));
-        tma_load_4d(brick, &tmap, &bar, oz, oy, ox, (int)blockIdx.z * 3);
+        box.commit(s_min, s_max, mxi, myi, mzi);
+        __syncthreads();
+        ox = s_min[0] - 1; oy = s_min[1] - 1; oz = (s_min[2] - 1) & ~3;           // lower corner index
+        fits = (s_max[0] - ox < BX) && (s_max[1] - oy < BY) && (s_max[2] - oz < BZ);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, 3u * CS * sizeof(float));
+            tma_load_4d(brick, &tmap, &bar, oz, oy, ox, (int)blockIdx.z * 3);
+        }
     }
     mbar_wait(&bar, 0);
 
@@ -154,7 +178,8 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
             o1[i * XS] = __fadd_rn(v1, a[1]);
             o2[i * XS] = __fadd_rn(v2, a[2]);
         };
-        if (nx == TX) {                               // interior thread: no predication in the loop
+        if (!ok_yz) return;
+        if (nx == TX) {                               // interior tile: no predication in the loop
 #pragma unroll
             for (int i = 0; i < TX; ++i) voxel(i);
         } else {
@@ -163,6 +188,7 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                 if (i < nx) voxel(i);
         }
     } else {
+        if (!ok_yz) return;
         const float *srcb = src + (size_t)blockIdx.z * 3 * Ns;
         const uint32_t GX = (uint32_t)Ys * Zs, GY = (uint32_t)Zs;
         for (int i = 0; i < nx; ++i) {
@@ -218,11 +244,11 @@ struct UpsampleArgs {
     int cap;                        // capacity (float4) of the coarse box in shared memory
 };
 
-template <int TX, int BX, int BY, int BZ, int FMODE>
+template <int TX, int BX, int BY, int BZ, int FMODE, bool HF>
 __global__ void __launch_bounds__(256)
 k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ img,
              const float *__restrict__ field, float *__restrict__ out, int Xi, int Yi, int Zi, int X, int Y,
-             int Z, int has_fill, float fill, int nzt, UpsampleArgs up) {
+             int Z, float fill, FastDiv nzt, UpsampleArgs up) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *brick = reinterpret_cast<float *>(smem_raw);   // [BX][BY][BZ]
     __shared__ __align__(8) uint64_t bar;
@@ -230,17 +256,20 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     constexpr int PX = BY * BZ, PY = BZ, CS = BX * BY * BZ;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int zt = blockIdx.x % nzt, yt = blockIdx.x / nzt;
+    const int yt = (int)fast_div(blockIdx.x, nzt), zt = (int)blockIdx.x - yt * (int)nzt.d;
     const int z = zt * TZ + lane, y = yt * TY + warp, x0 = blockIdx.y * TX;
     const bool ok_yz = (z < Z) && (y < Y);
+    // threads past the volume edge shadow the nearest voxel inside (loads and the bounding box run
+    // unpredicated; only their stores are masked)
+    const int zc = min(z, Z - 1), yc = min(y, Y - 1);
     const uint32_t N = (uint32_t)X * Y * Z, Ni = (uint32_t)Xi * Yi * Zi;
     const float *fb = field + (size_t)blockIdx.z * 3 * N;
     float *outb = out + (size_t)blockIdx.z * N;
     const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
     const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
-    const float fy = (float)y, fz = (float)z, fx0 = (float)x0;
-    const uint32_t vox0 = ((uint32_t)x0 * Y + y) * Z + z, XS = (uint32_t)Y * Z;
-    const int nx = ok_yz ? min(TX, X - x0) : 0;
+    const float fy = (float)yc, fz = (float)zc, fx0 = (float)x0;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + yc) * Z + zc, XS = (uint32_t)Y * Z;
+    const int nx = min(TX, X - x0);                       // CTA-uniform, >= 1
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -249,7 +278,7 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     }
     __syncthreads();
 
-    float l[3][TX];                                   // displacements, then sample locations
+    float l[3][TX];                                   // displacements, then CLIPPED sample locations
     if (FMODE == 2) {
         float4 *hbox = reinterpret_cast<float4 *>(smem_raw + (size_t)CS * sizeof(float));
         const int Xh = up.Xh, Yh = up.Yh, Zh = up.Zh;
@@ -272,8 +301,8 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             }
         }
         __syncthreads();
-        const AxisF ay = axis_fast(__ldg(up.cy + min(y, Y - 1)), (float)(Yh - 1), Yh - 1);
-        const AxisF az = axis_fast(__ldg(up.cz + min(z, Z - 1)), (float)(Zh - 1), Zh - 1);
+        const AxisF ay = axis_fast(__ldg(up.cy + yc), (float)(Yh - 1), Yh - 1);
+        const AxisF az = axis_fast(__ldg(up.cz + zc), (float)(Zh - 1), Zh - 1);
 #pragma unroll
         for (int i = 0; i < TX; ++i) {
             l[0][i] = l[1][i] = l[2][i] = 0.f;
@@ -307,32 +336,28 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     } else {
 #pragma unroll
         for (int i = 0; i < TX; ++i) {
-            if (i < nx) {
-                const uint32_t vox = vox0 + i * XS;
-                if (FMODE == 1) {
-                    l[0][i] = __ldg(fb + (size_t)vox * 3); l[1][i] = __ldg(fb + (size_t)vox * 3 + 1); l[2][i] = __ldg(fb + (size_t)vox * 3 + 2);
-                } else {
-                    l[0][i] = __ldg(fb + vox); l[1][i] = __ldg(fb + N + vox); l[2][i] = __ldg(fb + 2 * (size_t)N + vox);
-                }
+            const uint32_t vox = vox0 + min(i, nx - 1) * XS;
+            if (FMODE == 1) {
+                l[0][i] = __ldg(fb + (size_t)vox * 3); l[1][i] = __ldg(fb + (size_t)vox * 3 + 1); l[2][i] = __ldg(fb + (size_t)vox * 3 + 2);
             } else {
-                l[0][i] = l[1][i] = l[2][i] = 0.f;
+                l[0][i] = __ldg(fb + vox); l[1][i] = __ldg(fb + N + vox); l[2][i] = __ldg(fb + 2 * (size_t)N + vox);
             }
         }
     }
     BoxReduce box;
-    box.init();
+    uint32_t oob = 0;                                 // HF: voxels sampling outside the image
 #pragma unroll
     for (int i = 0; i < TX; ++i) {
-        l[0][i] = __fadd_rn(fx0 + (float)i, l[0][i]);
-        l[1][i] = __fadd_rn(fy, l[1][i]);
-        l[2][i] = __fadd_rn(fz, l[2][i]);
-        if (i < nx)
-            box.add(axis_fast_i1(l[0][i], mxf, mxi), axis_fast_i1(l[1][i], myf, myi), axis_fast_i1(l[2][i], mzf, mzi));
+        const float lx = __fadd_rn(fx0 + (float)min(i, nx - 1), l[0][i]);
+        const float ly = __fadd_rn(fy, l[1][i]);
+        const float lz = __fadd_rn(fz, l[2][i]);
+        if (HF && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) oob |= 1u << i;
+        l[0][i] = axis_clip(lx, mxf); l[1][i] = axis_clip(ly, myf); l[2][i] = axis_clip(lz, mzf);
+        if (i == 0) box.first(l[0][i], l[1][i], l[2][i]); else box.add(l[0][i], l[1][i], l[2][i]);
     }
-    box.commit(s_min, s_max, lane);
+    box.commit(s_min, s_max, mxi, myi, mzi);
     __syncthreads();
-    const int ox = s_min[0], oy = s_min[1], oz = s_min[2] & ~3;
-    if (ox == INT_MAX) return;
+    const int ox = s_min[0] - 1, oy = s_min[1] - 1, oz = (s_min[2] - 1) & ~3;     // lower corner index
     const bool fits = (s_max[0] - ox < BX) && (s_max[1] - oy < BY) && (s_max[2] - oz < BZ);
 
     if (fits) {                                       // a box that does not fit is not worth staging
@@ -342,17 +367,16 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
         }
         mbar_wait(&bar, 0);
     }
+    if (!ok_yz) return;
 
     const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
     if (fits) {
 #pragma unroll
         for (int i = 0; i < TX; i += 2) {
             if (i >= nx) break;
-            const bool hasB = i + 1 < nx;
-            const float lxa = l[0][i], lya = l[1][i], lza = l[2][i];
-            const float lxb = hasB ? l[0][i + 1] : lxa, lyb = hasB ? l[1][i + 1] : lya, lzb = hasB ? l[2][i + 1] : lza;
-            const AxisF ax = axis_fast(lxa, mxf, mxi), ay = axis_fast(lya, myf, myi), az = axis_fast(lza, mzf, mzi);
-            const AxisF bx = axis_fast(lxb, mxf, mxi), by = axis_fast(lyb, myf, myi), bz = axis_fast(lzb, mzf, mzi);
+            const bool hasB = i + 1 < nx;             // (the shadow of voxel i otherwise)
+            const AxisF ax = axis_from_clipped(l[0][i], mxi), ay = axis_from_clipped(l[1][i], myi), az = axis_from_clipped(l[2][i], mzi);
+            const AxisF bx = axis_from_clipped(l[0][i + 1], mxi), by = axis_from_clipped(l[1][i + 1], myi), bz = axis_from_clipped(l[2][i + 1], mzi);
             float wA[8], wB[8];
             tri_weights_pair(ax, ay, az, bx, by, bz, wA, wB);
             const float *qa = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
@@ -361,9 +385,9 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
             const float vb[8] = {qb[0], qb[1], qb[PY], qb[PY + 1], qb[PX], qb[PX + 1], qb[PX + PY], qb[PX + PY + 1]};
             float ra, rb;
             tri_accumulate_pair(wA, wB, va, vb, ra, rb);
-            if (has_fill) {
-                if (lxa < 0.f || lxa > mxf || lya < 0.f || lya > myf || lza < 0.f || lza > mzf) ra = fill;
-                if (lxb < 0.f || lxb > mxf || lyb < 0.f || lyb > myf || lzb < 0.f || lzb > mzf) rb = fill;
+            if (HF) {
+                if (oob & (1u << i)) ra = fill;
+                if (oob & (2u << i)) rb = fill;
             }
             outb[vox0 + i * XS] = ra;
             if (hasB) outb[vox0 + (i + 1) * XS] = rb;
@@ -374,13 +398,12 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
 #pragma unroll
         for (int i = 0; i < TX; ++i) {
             if (i >= nx) break;
-            const float lx = l[0][i], ly = l[1][i], lz = l[2][i];
-            const AxisF ax = axis_fast(lx, mxf, mxi), ay = axis_fast(ly, myf, myi), az = axis_fast(lz, mzf, mzi);
+            const AxisF ax = axis_from_clipped(l[0][i], mxi), ay = axis_from_clipped(l[1][i], myi), az = axis_from_clipped(l[2][i], mzi);
             float w[8], val[8];
             tri_weights(ax, ay, az, w);
             gather8(ib + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1)), GY, GX, 1u, val);
             float r = tri_accumulate(w, val);
-            if (has_fill && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) r = fill;
+            if (HF && (oob & (1u << i))) r = fill;
             outb[vox0 + i * XS] = r;
         }
     }
@@ -409,7 +432,7 @@ bool brick_eligible(const float *src, const float *own, const float *out, int Xs
 
 template <int TX, int BX, int BY, int BZ>
 static int launch_ss_brick_t(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
-                             int Y, int Z, float scale, cudaStream_t st) {
+                             int Y, int Z, float scale, const float *bound, float bscale, cudaStream_t st) {
     CUtensorMap tmap;
     if (!encode_map(&tmap, src, B * 3, Xs, Ys, Zs, BX, BY, BZ, 3)) return DFM_EUNSUPPORTED;
     constexpr size_t smem = 3ull * BX * BY * BZ * sizeof(float);
@@ -419,25 +442,30 @@ static int launch_ss_brick_t(const float *src, const float *own, float *out, int
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(k_ss_brick<TX, BX, BY, BZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_ss_brick smem attribute: %s", cudaGetErrorString(e));
+        if (const char *c = getenv("DFM_SS_CARVEOUT")) {                   // tuning aid: shared-memory carve-out, percent
+            cudaFuncSetAttribute(k_ss_brick<TX, BX, BY, BZ, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+            cudaFuncSetAttribute(k_ss_brick<TX, BX, BY, BZ, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+        }
         configured = true;
     }
     const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
     dim3 grid(nzt * nyt, nxt, B), block(256);
     if (scale == 1.f)
-        k_ss_brick<TX, BX, BY, BZ, false><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, nzt);
+        k_ss_brick<TX, BX, BY, BZ, false><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, make_fastdiv(nzt), bound, bscale);
     else
-        k_ss_brick<TX, BX, BY, BZ, true><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, nzt);
+        k_ss_brick<TX, BX, BY, BZ, true><<<grid, block, smem, st>>>(tmap, src, own, out, Xs, Ys, Zs, X, Y, Z, scale, make_fastdiv(nzt), bound, bscale);
     return check_launch("k_ss_brick");
 }
 
 int launch_ss_brick(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
-                    int Y, int Z, float scale, int large_box, cudaStream_t st) {
+                    int Y, int Z, float scale, int large_box, const float *bound, float bscale, cudaStream_t st) {
+    if (src != own) bound = nullptr;                  // the bound describes `own`, the box is cut from `src`
     // x/y extent = 8 (tile) + 1 (upper corner) + 1 (straddle) + deformation slack;
     // z pitch 64 = 32 + 1 + 1 + 3 (origin alignment) + slack, and bank-conflict free
     static const int cfg = getenv("DFM_BRICK_CFG") ? atoi(getenv("DFM_BRICK_CFG")) : 0;     // tuning aid
 #define DFM_SS(TXv, SX, SY, SZ, LX, LY, LZ)                                                                  \
-    return large_box ? launch_ss_brick_t<TXv, LX, LY, LZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st) \
-                     : launch_ss_brick_t<TXv, SX, SY, SZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, st)
+    return large_box ? launch_ss_brick_t<TXv, LX, LY, LZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, bound, bscale, st) \
+                     : launch_ss_brick_t<TXv, SX, SY, SZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, bound, bscale, st)
     switch (cfg) {
         case 1: DFM_SS(4, 6, 10, 40, 8, 12, 48);
         case 2: DFM_SS(4, 6, 10, 64, 8, 12, 64);
@@ -457,19 +485,32 @@ static int launch_warp_brick_t(const float *img, const float *field, float *out,
     constexpr size_t smem = (size_t)BX * BY * BZ * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick smem attribute: %s", cudaGetErrorString(e));
+        // Tiles whose box does not fit gather through L1.  Left alone, the driver sizes the carve-out for
+        // the 7 CTAs/SM the 30 KB brick allows and leaves almost no L1 (measured 1.45 ms on the bench
+        // field); 80 % (6 CTAs/SM, ~34 KB of L1) runs the same launch in 0.93 ms.
+        const int carve = getenv("DFM_WARP_CARVEOUT") ? atoi(getenv("DFM_WARP_CARVEOUT")) : 80;
+        cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         configured = true;
     }
     const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
     dim3 grid(nzt * nyt, nxt, B), block(256);
+    const FastDiv nz = make_fastdiv(nzt);
     UpsampleArgs none = {};
-    if (flags & DFM_FIELD_IN_CL)
-        k_warp_brick<TX, BX, BY, BZ, 1><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, none);
-    else
-        k_warp_brick<TX, BX, BY, BZ, 0><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, none);
+#define DFM_WB(FM, HFv) k_warp_brick<TX, BX, BY, BZ, FM, HFv><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, fill, nz, none)
+    if (flags & DFM_FIELD_IN_CL) {
+        if (has_fill) DFM_WB(1, true); else DFM_WB(1, false);
+    } else {
+        if (has_fill) DFM_WB(0, true); else DFM_WB(0, false);
+    }
+#undef DFM_WB
     return check_launch("k_warp_brick");
 }
 
@@ -489,13 +530,17 @@ static int launch_rescale_warp_t(const float *img, const float *half, float *out
     if (smem > 200 * 1024) return DFM_EUNSUPPORTED;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick(fused) smem attribute: %s", cudaGetErrorString(e));
         configured = smem;
     }
     const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
     dim3 grid(nzt * nyt, nxt, B), block(256);
-    k_warp_brick<TX, BX, BY, BZ, 2><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, has_fill, fill, nzt, up);
+    if (has_fill)
+        k_warp_brick<TX, BX, BY, BZ, 2, true><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, make_fastdiv(nzt), up);
+    else
+        k_warp_brick<TX, BX, BY, BZ, 2, false><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, make_fastdiv(nzt), up);
     return check_launch("k_warp_brick(fused rescale)");
 }
 

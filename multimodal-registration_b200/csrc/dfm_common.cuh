@@ -22,16 +22,33 @@ int check_launch(const char *what);
     } while (0)
 
 // planar out[b][c][n] = scale * in (3 channels; `in` planar or channels-last) -- dfm_layout.cu
-int scale_copy_to_planar(const float *in, float *out, int B, size_t N, float scale, bool in_cl,
+// absmax (nullable): float per batch item, zeroed by the caller; receives max |out| of the item
+int scale_copy_to_planar(const float *in, float *out, int B, size_t N, float scale, bool in_cl, float *absmax,
                          cudaStream_t st);
+
+// running max |v|; a NaN counts as +inf (it sticks, and only disables the static halo)
+__device__ __forceinline__ float absmax_fold(float m, float v) { return v != v ? __int_as_float(0x7f800000) : fmaxf(m, fabsf(v)); }
+// block-wide max of a non-negative float, folded into *dst by one atomic per CTA (float bits order
+// like ints for values >= 0).
+// Must be reached by every thread of the block.
+__device__ __forceinline__ void block_absmax_commit(float m, float *dst) {
+    __shared__ int s_m;
+    if (threadIdx.x == 0) s_m = 0;
+    __syncthreads();
+    atomicMax(&s_m, __float_as_int(m));
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<int *>(dst), s_m);
+}
 
 int validate_grid(const char *who, int B, int X, int Y, int Z);
 
 // TMA-brick path of out = scale*own + interp(scale*src, p + scale*own) -- dfm_brick.cu
 bool brick_eligible(const float *src, const float *own, const float *out, int Xs, int Ys, int Zs, int X,
                     int Y, int Z, unsigned flags);
+// `bound` (nullable, device, one float per batch item) with `bscale`: bound[b] * bscale is an upper
+// bound of |own| for item b; displacements below the brick's static halo skip the box reduction
 int launch_ss_brick(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
-                    int Y, int Z, float scale, int large_box, cudaStream_t st);
+                    int Y, int Z, float scale, int large_box, const float *bound, float bscale, cudaStream_t st);
 // TMA-brick path of the one-channel linear image warp (returns DFM_EUNSUPPORTED if not applicable)
 int launch_warp_brick(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
                       int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st);
@@ -143,6 +160,16 @@ __device__ __forceinline__ AxisF axis_fast(float loc, float maxf, int maxi) {
 }
 __device__ __forceinline__ int axis_fast_i1(float loc, float maxf, int maxi) {
     return min(__float2int_rz(fminf(fmaxf(loc, 0.f), maxf)) + 1, maxi);
+}
+// the same set-up split in two, for kernels that clip once and keep the clipped location
+__device__ __forceinline__ float axis_clip(float loc, float maxf) { return fminf(fmaxf(loc, 0.f), maxf); }
+__device__ __forceinline__ int axis_clipped_i1(float cl, int maxi) { return min(__float2int_rz(cl) + 1, maxi); }
+__device__ __forceinline__ AxisF axis_from_clipped(float cl, int maxi) {
+    AxisF a;
+    a.i1 = min(__float2int_rz(cl) + 1, maxi);
+    a.w0 = __fsub_rn((float)a.i1, cl);
+    a.w1 = __fsub_rn(1.f, a.w0);
+    return a;
 }
 __device__ __forceinline__ void tri_weights(const AxisF &ax, const AxisF &ay, const AxisF &az, float (&w)[8]) {
     const float w00 = __fmul_rn(ax.w0, ay.w0), w01 = __fmul_rn(ax.w0, ay.w1);

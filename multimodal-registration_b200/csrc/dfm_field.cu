@@ -17,10 +17,10 @@ template <int ROWS, int INTERP, bool IN_CL, bool OUT_CL>
 __global__ void __launch_bounds__(256, 4)
 k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, float *__restrict__ out,
                  int Xs, int Ys, int Zs, int X, int Y, int Z, float scale, FastDiv zdiv,
-                 uint32_t plane_items) {
+                 uint32_t plane_items, float *absmax) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= plane_items) return;
-    const uint32_t yy = fast_div(p, zdiv);
+    const uint32_t yy = p < plane_items ? fast_div(p, zdiv) : 0xffffffffu / ROWS;      // past the end: no rows
+    float am = 0.f;                                                  // max |out| (absmax != nullptr)
     const uint32_t z = p - yy * zdiv.d;
     const uint32_t x = blockIdx.y;
     const uint32_t N = (uint32_t)X * Y * Z, Ns = (uint32_t)Xs * Ys * Zs;
@@ -80,12 +80,14 @@ k_field_warp_add(const float *__restrict__ src, const float *__restrict__ own, f
         const float r0 = __fadd_rn(v0, __fmul_rn(scale, a0));
         const float r1 = __fadd_rn(v1, __fmul_rn(scale, a1));
         const float r2 = __fadd_rn(v2, __fmul_rn(scale, a2));
+        am = absmax_fold(absmax_fold(absmax_fold(am, r0), r1), r2);
         if (OUT_CL) {
             outb[(size_t)vox * 3] = r0; outb[(size_t)vox * 3 + 1] = r1; outb[(size_t)vox * 3 + 2] = r2;
         } else {
             outb[vox] = r0; outb[N + vox] = r1; outb[2 * (size_t)N + vox] = r2;
         }
     }
+    if (absmax) block_absmax_commit(am, absmax + blockIdx.z);        // uniform branch
 }
 
 // planar linear variant written for memory-level parallelism (see k_warp_linear1): all 24 corner
@@ -142,14 +144,14 @@ static int launch_fwa1(const float *src, const float *own, float *out, int B, in
 
 template <int INTERP>
 static int launch_fwa(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs,
-                      int X, int Y, int Z, float scale, unsigned flags, cudaStream_t st) {
+                      int X, int Y, int Z, float scale, unsigned flags, cudaStream_t st, float *absmax = nullptr) {
     constexpr int ROWS = 4;
     const uint32_t plane = (uint32_t)((Y + ROWS - 1) / ROWS) * Z;
     dim3 grid((plane + 255) / 256, X, B), block(256);
     FastDiv fd = make_fastdiv(Z);
     const bool icl = flags & DFM_FIELD_IN_CL, ocl = flags & DFM_FIELD_OUT_CL;
 #define DFM_GO(I, O) k_field_warp_add<ROWS, INTERP, I, O><<<grid, block, 0, st>>>( \
-        src, own, out, Xs, Ys, Zs, X, Y, Z, scale, fd, plane)
+        src, own, out, Xs, Ys, Zs, X, Y, Z, scale, fd, plane, absmax)
     if (icl) { if (ocl) DFM_GO(true, true); else DFM_GO(true, false); }
     else     { if (ocl) DFM_GO(false, true); else DFM_GO(false, false); }
 #undef DFM_GO
@@ -184,7 +186,7 @@ extern "C" int dfm_field_warp_add(const float *src, const float *own, float *out
     if (interp == DFM_LINEAR) {
         if (brick_eligible(src, own, out, Xs, Ys, Zs, X, Y, Z, flags)) {
             // a stand-alone call (compose, a single SS step) sees full-size displacements: larger brick
-            rc = launch_ss_brick(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, /*large_box=*/1, st);
+            rc = launch_ss_brick(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, /*large_box=*/1, nullptr, 0.f, st);
             if (rc != DFM_EUNSUPPORTED) return rc;
         }
         if (!(flags & DFM_FIELD_IN_CL) && Xs >= 2 && Ys >= 2 && Zs >= 2)
@@ -197,24 +199,27 @@ extern "C" int dfm_field_warp_add(const float *src, const float *own, float *out
 extern "C" size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nsteps, int save_steps) {
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || nsteps <= 0) return 0;
     const size_t one = (size_t)B * 3 * X * Y * Z * sizeof(float);
-    if (save_steps) return one * (size_t)nsteps;
-    return nsteps >= 2 ? one : 0;
+    const size_t bound = ((size_t)B * sizeof(float) + 255) / 256 * 256;     // per-item displacement bound (static halo)
+    if (save_steps) return one * (size_t)nsteps + bound;
+    return nsteps >= 2 ? one + bound : 0;
 }
 
 // one SS step with the implementation choice: late steps (large displacements, stronger local
 // deformation) get the larger brick
+// bound/bscale: see launch_ss_brick; absmax (nullable): receives max |vout| per item when the step runs on the
+// gather kernel (channels-last input -- the first step of an inference call)
 static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, float scale, unsigned flags,
-                   int steps_left, cudaStream_t st) {
+                   int steps_left, const float *bound, float bscale, float *absmax, cudaStream_t st) {
     static const bool prefer_direct = getenv("DFM_SS_DIRECT") != nullptr;      // tuning aid
     if (prefer_direct && !(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
         return launch_fwa1(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
     if (brick_eligible(vin, vin, vout, X, Y, Z, X, Y, Z, flags)) {
-        int rc = launch_ss_brick(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, steps_left < 2 ? 1 : 0, st);
+        int rc = launch_ss_brick(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, steps_left < 2 ? 1 : 0, bound, bscale, st);
         if (rc != DFM_EUNSUPPORTED) return rc;
     }
     if (!(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
         return launch_fwa1(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
-    return launch_fwa<DFM_LINEAR>(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
+    return launch_fwa<DFM_LINEAR>(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st, absmax);
 }
 
 extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, int X, int Y, int Z,
@@ -240,27 +245,39 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
     const size_t need = dfm_vecint_workspace_bytes(B, X, Y, Z, nsteps, save_steps);
     DFM_REQUIRE(need == 0 || work, DFM_EINVAL, "dfm_vecint_fwd: workspace of %zu bytes required", need);
     const float scale0 = ldexpf(1.f, -nsteps);
+    // |v_{k+1}| <= 2 max|v_k| (v_{k+1} = v_k + a convex combination of v_k), so one measured maximum
+    // bounds every later step: steps whose bound is below the brick's static halo skip the box reduction
+    float *bound = work ? work + (save_steps ? (size_t)nsteps : (size_t)1) * n : nullptr;
     if (save_steps) {
         // work[k] = v_k (input of step k), k = 0..nsteps-1; v_0 = svf * 2^-nsteps (planar)
-        rc = scale_copy_to_planar(svf, work, B, (size_t)X * Y * Z, scale0, in_cl != 0, st);
+        cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)B * sizeof(float), st);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "dfm_vecint_fwd: %s", cudaGetErrorString(e));
+        rc = scale_copy_to_planar(svf, work, B, (size_t)X * Y * Z, scale0, in_cl != 0, bound, st);   // bound = max|v_0|
         if (rc) return rc;
         for (int k = 0; k < nsteps; ++k) {
             const float *vin = work + (size_t)k * n;
             float *vout = (k == nsteps - 1) ? out : work + (size_t)(k + 1) * n;
             unsigned f = (k == nsteps - 1) ? out_cl : 0u;
-            rc = ss_step(vin, vout, B, X, Y, Z, 1.f, f, nsteps - 1 - k, st);
+            rc = ss_step(vin, vout, B, X, Y, Z, 1.f, f, nsteps - 1 - k, bound, ldexpf(1.f, k), nullptr, st);
             if (rc) return rc;
         }
         return DFM_OK;
     }
-    // ping-pong between `work` and `out` so that the last step lands in `out`; intermediates planar
+    // ping-pong between `work` and `out` so that the last step lands in `out`; intermediates planar.
+    // A channels-last svf goes through the gather kernel first, which measures max|v_1| on the way.
+    const bool measured = in_cl && nsteps >= 2;
+    if (measured) {
+        cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)B * sizeof(float), st);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "dfm_vecint_fwd: %s", cudaGetErrorString(e));
+    }
     const float *cur = svf;
     unsigned cur_cl = in_cl;
     for (int k = 0; k < nsteps; ++k) {
         const bool last = (k == nsteps - 1);
         float *dst = ((nsteps - 1 - k) % 2 == 0) ? out : work;
         unsigned f = cur_cl | (last ? out_cl : 0u);
-        rc = ss_step(cur, dst, B, X, Y, Z, k == 0 ? scale0 : 1.f, f, nsteps - 1 - k, st);
+        rc = ss_step(cur, dst, B, X, Y, Z, k == 0 ? scale0 : 1.f, f, nsteps - 1 - k,
+                     (measured && k >= 1) ? bound : nullptr, ldexpf(1.f, k - 1), (measured && k == 0) ? bound : nullptr, st);
         if (rc) return rc;
         cur = dst;
         cur_cl = 0u;

@@ -57,19 +57,27 @@ static int transpose(const void *in, void *out, int B, int C, size_t N, int elem
 
 template <bool IN_CL>
 __global__ void __launch_bounds__(256)
-k_scale_copy3(const float *__restrict__ in, float *__restrict__ out, size_t N, float scale) {
+k_scale_copy3(const float *__restrict__ in, float *__restrict__ out, size_t N, float scale, float *absmax) {
     const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float *ib = in + (size_t)blockIdx.y * 3 * N;
-    float *ob = out + (size_t)blockIdx.y * 3 * N;
+    float m = 0.f;
+    if (n < N) {
+        const float *ib = in + (size_t)blockIdx.y * 3 * N;
+        float *ob = out + (size_t)blockIdx.y * 3 * N;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) ob[c * N + n] = scale * (IN_CL ? ib[n * 3 + c] : ib[c * N + n]);
+        for (int c = 0; c < 3; ++c) {
+            const float v = scale * (IN_CL ? ib[n * 3 + c] : ib[c * N + n]);
+            ob[c * N + n] = v;
+            m = absmax_fold(m, v);
+        }
+    }
+    if (absmax) block_absmax_commit(m, absmax + blockIdx.y);
 }
 
-int scale_copy_to_planar(const float *in, float *out, int B, size_t N, float scale, bool in_cl, cudaStream_t st) {
+int scale_copy_to_planar(const float *in, float *out, int B, size_t N, float scale, bool in_cl, float *absmax,
+                         cudaStream_t st) {
     dim3 grid((unsigned)((N + 255) / 256), B), block(256);
-    if (in_cl) k_scale_copy3<true><<<grid, block, 0, st>>>(in, out, N, scale);
-    else k_scale_copy3<false><<<grid, block, 0, st>>>(in, out, N, scale);
+    if (in_cl) k_scale_copy3<true><<<grid, block, 0, st>>>(in, out, N, scale, absmax);
+    else k_scale_copy3<false><<<grid, block, 0, st>>>(in, out, N, scale, absmax);
     return check_launch("scale_copy_to_planar");
 }
 

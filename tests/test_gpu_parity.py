@@ -256,7 +256,8 @@ def test_transform_model_and_vxmdense_tail():
     # VxmDense tail: svf at half res -> VecInt(5) -> x2 -> linear warp; second output = preint flow
     fused = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2, fuse_rescale_warp=True)
     model = vxm.networks.VxmDense((8, 12, 16), int_steps=5, svf_resolution=2, int_resolution=2)
-    np.testing.assert_array_equal(fused.predict_deform([scan, half])[0], model.predict_deform([scan, half])[0])
+    # fused = unfused bit for bit in the exact build; the fast build's up-sampler is separable (few ulp)
+    assert_linear_parity(fused.predict_deform([scan, half])[0], model.predict_deform([scan, half])[0])
     assert fused.references.pos_flow is None
     y, pre = model.predict_deform([scan, half])
     model.deform([scan, half])          # keeps references.pos_flow (predict_deform may fuse it away)
@@ -332,7 +333,12 @@ def test_fused_rescale_warp_matches_unfused_bitwise():
             fused = host(ops.rescale_warp(dev(scan), dev(half, 'planar'), 2, fv))
             flow = ops.rescale_dense_transform(dev(half, 'planar'), 2)
             unfused = host(ops.warp(dev(scan), flow, 'linear', fv))
-            np.testing.assert_array_equal(fused, unfused)           # same arithmetic, either build
+            if mrb._lib.exact_order():
+                np.testing.assert_array_equal(fused, unfused)       # same arithmetic
+            elif fv is None:
+                assert_linear_parity(fused, unfused)                # fast build: the stand-alone up-sampler is separable
+            else:                                                   # a few-ulp flow change can flip a voxel across the fill boundary
+                assert np.mean(~np.isclose(fused, unfused, rtol=RTOL, atol=ATOL)) < 1e-3
             assert_linear_parity(fused, io.spatial_transformer(scan, io.rescale_dense_transform(half, 2), 'linear', fv))
 
 
