@@ -150,6 +150,10 @@ extern "C" int dfm_warp_bwd(const float *gout, const float *img, const float *fi
     DFM_REQUIRE(gout && img && field, DFM_EINVAL, "dfm_warp_bwd: null pointer");
     if (C == 1) flags &= ~DFM_IMG_CL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (C > 1 && (flags & DFM_IMG_CL)) {      // channels-last multi-channel: lanes over channels
+        int rc = launch_warp_cl_bwd(gout, img, field, gimg, gfield, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, flags, st);
+        if (rc != DFM_EUNSUPPORTED) return rc;
+    }
     if (!gimg && gfield && flags == 0u) {     // d/dfield only, all planar: TMA channel ring, no atomics
         int rc = launch_warp_mc_bwd_field(gout, img, field, gfield, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, st);
         if (rc != DFM_EUNSUPPORTED) return rc;

@@ -304,6 +304,10 @@ extern "C" int dfm_warp_fwd(const void *img, const float *field, void *out, int 
             int rc = launch_warp_brick((const float *)img, field, (float *)out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
             if (rc != DFM_EUNSUPPORTED) return rc;
         }
+        if (C > 1 && (flags & DFM_IMG_CL)) {   // channels-last multi-channel (the reference layout): lanes over channels
+            int rc = launch_warp_cl_fwd((const float *)img, field, (float *)out, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+            if (rc != DFM_EUNSUPPORTED) return rc;
+        }
         if (C > 1 && !(flags & (DFM_IMG_CL | DFM_FIELD_IN_CL | DFM_LOC_ABSOLUTE))) {   // planar multi-channel: TMA channel ring
             int rc = launch_warp_mc_fwd((const float *)img, field, (float *)out, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, fill, st);
             if (rc != DFM_EUNSUPPORTED) return rc;

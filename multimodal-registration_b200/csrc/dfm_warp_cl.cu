@@ -1,0 +1,321 @@
+// Channels-last multi-channel linear warp, forward and backward (the reference's own layout:
+// SpatialTransformer('linear')([one_hot(26), flow]) at train_synthmorph.py:298).
+//
+// With the channels innermost, the C values of one corner are one contiguous run (104 bytes at
+// C = 26), so a gather is a coalesced line read instead of 32 scattered words.  The kernels use
+// the lanes of a warp for the CHANNELS:
+//   phase A  lane = voxel: the warp's 32 consecutive voxels load their displacement (coalesced),
+//            set up corner base / weights once and park them in shared memory;
+//   phase B  lane = channel: for each of the 32 voxels the record is broadcast back (3-4 LDS.128)
+//            and every lane gathers its channel of the 8 corners; small channel counts put
+//            32 / Cpad voxels side by side in the warp, large ones loop over 32-channel chunks.
+// Backward: d/d field sums over channels with a warp reduction (no atomics); d/d img scatters
+// with coalesced float atomics (reference semantics: gather back-propagates as scatter-add).
+// Arithmetic per value is the shared tri_weights / tri_accumulate, so the forward pass is
+// bit-identical to the other linear kernels in both builds.
+#include "dfm_common.cuh"
+
+namespace dfm {
+
+struct __align__(16) FwdRec {
+    float w[8];
+    uint32_t base;      // element index of corner (0,0,0), channel 0
+    uint32_t dead;      // fill_value applies
+    uint32_t pad[2];
+};
+
+// opaque move: keeps a warp-uniform value in a vector register (the compiler would otherwise hold it
+// in a uniform register, which the 64-bit address arithmetic cannot take as the 32-bit multiplicand)
+__device__ __forceinline__ uint32_t vreg(uint32_t x) {
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+__device__ __forceinline__ void voxel_xyz(uint32_t n, FastDiv zdiv, FastDiv ydiv, uint32_t &x, uint32_t &y, uint32_t &z) {
+    const uint32_t q = fast_div(n, zdiv);
+    z = n - q * zdiv.d;
+    x = fast_div(q, ydiv);
+    y = q - x * ydiv.d;
+}
+
+// phase A shared by forward and backward: sample location of voxel n (lane = voxel)
+__device__ __forceinline__ void load_loc(const float *__restrict__ fb, uint32_t n, uint32_t N, bool field_cl, bool absolute,
+                                         FastDiv zdiv, FastDiv ydiv, float &lx, float &ly, float &lz) {
+    if (field_cl) { lx = __ldg(fb + (size_t)n * 3); ly = __ldg(fb + (size_t)n * 3 + 1); lz = __ldg(fb + (size_t)n * 3 + 2); }
+    else { lx = __ldg(fb + n); ly = __ldg(fb + N + n); lz = __ldg(fb + 2 * (size_t)N + n); }
+    if (!absolute) {
+        uint32_t x, y, z;
+        voxel_xyz(n, zdiv, ydiv, x, y, z);
+        lx = __fadd_rn((float)x, lx); ly = __fadd_rn((float)y, ly); lz = __fadd_rn((float)z, lz);
+    }
+}
+
+// CSHIFT: log2 of the lanes per voxel (Cpad >= C, or 32 with MULTI = loop over 32-channel chunks)
+template <int CSHIFT, bool MULTI, bool HF>
+__global__ void __launch_bounds__(256)
+k_warp_cl(const float *__restrict__ img, const float *__restrict__ field, float *__restrict__ out, int C, int Xi,
+          int Yi, int Zi, uint32_t N, float fill, int field_cl, int absolute, FastDiv zdiv, FastDiv ydiv) {
+    __shared__ FwdRec s_rec[8][32];
+    constexpr int CPAD = 1 << CSHIFT, VPW = 32 >> CSHIFT;           // voxels side by side in the warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n0 = blockIdx.x * 256u + warp * 32u;          // first voxel of this warp
+    if (n0 >= N) return;
+    const uint32_t Ni = (uint32_t)Xi * Yi * Zi;
+    const float *ib = img + (size_t)blockIdx.y * C * Ni;
+    {   // ---- phase A: lane = voxel ---------------------------------------------------------
+        const uint32_t n = min(n0 + lane, N - 1);
+        float lx, ly, lz;
+        load_loc(field + (size_t)blockIdx.y * 3 * N, n, N, field_cl, absolute, zdiv, ydiv, lx, ly, lz);
+        const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
+        const AxisF ax = axis_fast(lx, (float)mxi, mxi), ay = axis_fast(ly, (float)myi, myi), az = axis_fast(lz, (float)mzi, mzi);
+        FwdRec r;
+        tri_weights(ax, ay, az, r.w);
+        r.base = (((uint32_t)(ax.i1 - 1) * Yi + (uint32_t)(ay.i1 - 1)) * Zi + (uint32_t)(az.i1 - 1)) * (uint32_t)C;
+        r.dead = HF && (lx < 0.f || lx > (float)mxi || ly < 0.f || ly > (float)myi || lz < 0.f || lz > (float)mzi);
+        r.pad[0] = r.pad[1] = 0;
+        s_rec[warp][lane] = r;
+    }
+    __syncwarp();
+    // ---- phase B: lane = channel -------------------------------------------------------------
+    const int sub = lane >> CSHIFT, c0 = lane & (CPAD - 1);
+    // corner offsets kept in vector registers: address = IMAD.WIDE.U32(offset, 4, p), one instruction per load
+    const uint32_t oC = vreg((uint32_t)C), oZ = vreg((uint32_t)Zi * C), oY = vreg((uint32_t)Yi * Zi * C);
+    const uint32_t o3 = vreg(oZ + oC), o5 = vreg(oY + oC), o6 = vreg(oY + oZ), o7 = vreg(oY + oZ + oC);
+    const bool lane_on = MULTI || c0 < C;
+    const uint32_t nv = min(32u, N - n0);                             // voxels of this warp (warp-uniform)
+    float *po = out + (size_t)blockIdx.y * C * N + (size_t)n0 * C + (uint32_t)sub * oC + c0;
+    const float *pi = ib + c0;
+#pragma unroll 4
+    for (int j0 = 0; j0 < 32; j0 += VPW, po += VPW * oC) {
+        const int j = j0 + sub;
+        if ((uint32_t)j >= nv || !lane_on) continue;
+        const FwdRec r = s_rec[warp][j];
+        const float *p = pi + r.base;
+        if (MULTI) {
+            for (int c = c0; c < C; c += 32) {
+                const float *q = p + (c - c0);
+                const float v[8] = {__ldg(q), __ldg(q + oC), __ldg(q + oZ), __ldg(q + o3),
+                                    __ldg(q + oY), __ldg(q + o5), __ldg(q + o6), __ldg(q + o7)};
+                float a = tri_accumulate(r.w, v);
+                if (HF && r.dead) a = fill;
+                po[c - c0] = a;
+            }
+        } else {
+            const float v[8] = {__ldg(p), __ldg(p + oC), __ldg(p + oZ), __ldg(p + o3),
+                                __ldg(p + oY), __ldg(p + o5), __ldg(p + o6), __ldg(p + o7)};
+            float a = tri_accumulate(r.w, v);
+            if (HF && r.dead) a = fill;
+            *po = a;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) BwdRec {
+    float dx[4];        // m_x * wy[b] * wz[c]   (index b*2+c): weight of (v[1,b,c] - v[0,b,c])
+    float dy[4];        // m_y * wx[a] * wz[c]   (index a*2+c)
+    float dz[4];        // m_z * wx[a] * wy[b]   (index a*2+b)
+    uint32_t base;
+    uint32_t pad[3];
+};
+
+// sum of three per-lane values over the 2^cshift lanes of a voxel; every lane of the group gets the sums
+__device__ __forceinline__ void group_sum3(float &a, float &b, float &c, int cshift) {
+    for (int o = (1 << cshift) >> 1; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+}
+// the same over the whole warp with 6 shuffles instead of 15: after two folding steps every lane
+// carries one of the three sums, three more steps finish it; lane (q << 3) holds sum q on return
+__device__ __forceinline__ float warp_sum3_folded(float a, float b, float c, int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8;
+    // step 1 (xor 16): lower half keeps (a, b), upper half keeps (c, 0)
+    const float s1 = __shfl_xor_sync(0xffffffffu, up16 ? a : c, 16);
+    const float s2 = __shfl_xor_sync(0xffffffffu, up16 ? b : 0.f, 16);
+    float p = up16 ? c + s1 : a + s1;         // a (lower) | c (upper)
+    float q = up16 ? s2 : b + s2;             // b (lower) | 0 + (partner's 0) (upper)
+    // step 2 (xor 8): lanes with bit 3 clear keep p, the others keep q
+    const float s3 = __shfl_xor_sync(0xffffffffu, up8 ? p : q, 8);
+    float r = up8 ? q + s3 : p + s3;          // bits (4,3): 00 a, 01 b, 10 c, 11 0
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+template <int CSHIFT, bool MULTI, bool NEED_IMG, bool NEED_FIELD>
+__global__ void __launch_bounds__(256)
+k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ field,
+              float *__restrict__ gimg, float *__restrict__ gfield, int C, int Xi, int Yi, int Zi, uint32_t N,
+              int has_fill, int field_cl, int gfield_cl, FastDiv zdiv, FastDiv ydiv) {
+    __shared__ BwdRec s_rec[8][32];
+    __shared__ __align__(16) float s_w[NEED_IMG ? 8 : 1][32][8];
+    constexpr int CPAD = 1 << CSHIFT, VPW = 32 >> CSHIFT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n0 = blockIdx.x * 256u + warp * 32u;
+    if (n0 >= N) return;
+    const uint32_t Ni = (uint32_t)Xi * Yi * Zi;
+    {
+        const uint32_t n = min(n0 + lane, N - 1);
+        float lx, ly, lz;
+        load_loc(field + (size_t)blockIdx.y * 3 * N, n, N, field_cl, false, zdiv, ydiv, lx, ly, lz);
+        const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
+        const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+        const AxisF ax = axis_fast(lx, mxf, mxi), ay = axis_fast(ly, myf, myi), az = axis_fast(lz, mzf, mzi);
+        const bool dead = has_fill && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf);
+        // clip passes the gradient on [0, max]; at loc == max both reference corners are the edge voxel
+        // (difference 0), which the i1 - 1 addressing reproduces with a strict upper bound
+        const float gx = (!dead && lx >= 0.f && lx < mxf) ? 1.f : 0.f;
+        const float gy = (!dead && ly >= 0.f && ly < myf) ? 1.f : 0.f;
+        const float gz = (!dead && lz >= 0.f && lz < mzf) ? 1.f : 0.f;
+        const float wx[2] = {ax.w0, ax.w1}, wy[2] = {ay.w0, ay.w1}, wz[2] = {az.w0, az.w1};
+        BwdRec r;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                r.dx[p * 2 + q] = gx * wy[p] * wz[q];
+                r.dy[p * 2 + q] = gy * wx[p] * wz[q];
+                r.dz[p * 2 + q] = gz * wx[p] * wy[q];
+            }
+        r.base = (((uint32_t)(ax.i1 - 1) * Yi + (uint32_t)(ay.i1 - 1)) * Zi + (uint32_t)(az.i1 - 1)) * (uint32_t)C;
+        r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        s_rec[warp][lane] = r;
+        if (NEED_IMG) {
+            float w[8];
+            tri_weights(ax, ay, az, w);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_w[warp][lane][k] = dead ? 0.f : w[k];
+        }
+    }
+    __syncwarp();
+    const int sub = lane >> CSHIFT, c0 = lane & (CPAD - 1);
+    const uint32_t oC = (uint32_t)C, oZ = (uint32_t)Zi * C, oY = (uint32_t)Yi * Zi * C;
+    const uint32_t o3 = oZ + oC, o5 = oY + oC, o6 = oY + oZ, o7 = oY + oZ + oC;
+    const bool lane_on = MULTI || c0 < C;
+    const uint32_t nv = min(32u, N - n0);
+    const float *pg = gout + (size_t)blockIdx.y * C * N + (size_t)n0 * C + (uint32_t)sub * oC + c0;
+    const float *pi = img + (size_t)blockIdx.y * C * Ni + c0;
+    float *pq = NEED_IMG ? gimg + (size_t)blockIdx.y * C * Ni + c0 : nullptr;
+    float mine[3] = {0.f, 0.f, 0.f};                       // gradient of voxel n0 + lane
+#pragma unroll 2
+    for (int j0 = 0; j0 < 32; j0 += VPW, pg += VPW * oC) {
+        const int j = j0 + sub;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if ((uint32_t)j < nv && lane_on) {
+            const BwdRec r = s_rec[warp][j];
+            for (int cc = 0; cc < (MULTI ? C - c0 : 1); cc += 32) {
+                const float g = __ldg(pg + cc);
+                if (NEED_FIELD) {
+                    const float *p = pi + r.base + cc;
+                    const float v[8] = {__ldg(p), __ldg(p + oC), __ldg(p + oZ), __ldg(p + o3),
+                                        __ldg(p + oY), __ldg(p + o5), __ldg(p + o6), __ldg(p + o7)};
+                    float dx = r.dx[0] * (v[4] - v[0]);
+                    dx = fmaf(r.dx[1], v[5] - v[1], dx); dx = fmaf(r.dx[2], v[6] - v[2], dx); dx = fmaf(r.dx[3], v[7] - v[3], dx);
+                    float dy = r.dy[0] * (v[2] - v[0]);
+                    dy = fmaf(r.dy[1], v[3] - v[1], dy); dy = fmaf(r.dy[2], v[6] - v[4], dy); dy = fmaf(r.dy[3], v[7] - v[5], dy);
+                    float dz = r.dz[0] * (v[1] - v[0]);
+                    dz = fmaf(r.dz[1], v[3] - v[2], dz); dz = fmaf(r.dz[2], v[5] - v[4], dz); dz = fmaf(r.dz[3], v[7] - v[6], dz);
+                    sx = fmaf(g, dx, sx); sy = fmaf(g, dy, sy); sz = fmaf(g, dz, sz);
+                }
+                if (NEED_IMG) {
+                    float *q = pq + r.base + cc;
+                    const float4 wa = *reinterpret_cast<const float4 *>(&s_w[warp][j][0]);
+                    const float4 wb = *reinterpret_cast<const float4 *>(&s_w[warp][j][4]);
+                    const uint32_t off[8] = {0u, oC, oZ, o3, oY, o5, o6, o7};
+                    const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float a = w[k] * g;
+                        if (a != 0.f) atomicAdd(q + off[k], a);
+                    }
+                }
+            }
+        }
+        if (NEED_FIELD) {
+            if (CSHIFT == 5) {
+                const float s = warp_sum3_folded(sx, sy, sz, lane);          // lane 0: x, 8: y, 16: z
+                const float tx = __shfl_sync(0xffffffffu, s, 0), ty = __shfl_sync(0xffffffffu, s, 8),
+                            tz = __shfl_sync(0xffffffffu, s, 16);
+                if (lane == j0) { mine[0] = tx; mine[1] = ty; mine[2] = tz; }
+            } else {
+                group_sum3(sx, sy, sz, CSHIFT);
+                const int src = ((lane - j0) & (VPW - 1)) << CSHIFT;       // group of voxel j0 + (lane - j0)
+                const float tx = __shfl_sync(0xffffffffu, sx, src), ty = __shfl_sync(0xffffffffu, sy, src),
+                            tz = __shfl_sync(0xffffffffu, sz, src);
+                if (lane >= j0 && lane < j0 + VPW) { mine[0] = tx; mine[1] = ty; mine[2] = tz; }
+            }
+        }
+    }
+    if (NEED_FIELD) {
+        const uint32_t n = n0 + lane;
+        if (n < N) {
+            float *gf = gfield + (size_t)blockIdx.y * 3 * N;
+            if (gfield_cl) { gf[(size_t)n * 3] = mine[0]; gf[(size_t)n * 3 + 1] = mine[1]; gf[(size_t)n * 3 + 2] = mine[2]; }
+            else { gf[n] = mine[0]; gf[N + n] = mine[1]; gf[2 * (size_t)N + n] = mine[2]; }
+        }
+    }
+}
+
+// ------------------------------- host side -----------------------------------------------
+static bool cl_ok(int C, int Xi, int Yi, int Zi) {
+    static const bool off = getenv("DFM_NO_WARP_CL") != nullptr;          // tuning aid
+    return !off && C > 1 && Xi >= 2 && Yi >= 2 && Zi >= 2 && (uint64_t)Xi * Yi * Zi * (uint64_t)C < (1ull << 31);
+}
+static int cpad_shift(int C) {
+    int s = 0;
+    while ((1 << s) < C && s < 5) ++s;
+    return s;
+}
+
+int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
+                       int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
+    if (!cl_ok(C, Xi, Yi, Zi) || (uint64_t)X * Y * Z * (uint64_t)C >= (1ull << 31)) return DFM_EUNSUPPORTED;
+    const uint32_t N = (uint32_t)X * Y * Z;
+    dim3 grid((N + 255) / 256, B), block(256);
+    const FastDiv zd = make_fastdiv(Z), yd = make_fastdiv(Y);
+    const int fcl = (flags & DFM_FIELD_IN_CL) ? 1 : 0, ab = (flags & DFM_LOC_ABSOLUTE) ? 1 : 0;
+#define DFM_GO(S, M, H) k_warp_cl<S, M, H><<<grid, block, 0, st>>>(img, field, out, C, Xi, Yi, Zi, N, fill, fcl, ab, zd, yd)
+#define DFM_GO2(S, M) do { if (has_fill) DFM_GO(S, M, true); else DFM_GO(S, M, false); } while (0)
+    if (C > 32) DFM_GO2(5, true);
+    else switch (cpad_shift(C)) {
+        case 1: DFM_GO2(1, false); break;
+        case 2: DFM_GO2(2, false); break;
+        case 3: DFM_GO2(3, false); break;
+        case 4: DFM_GO2(4, false); break;
+        default: DFM_GO2(5, false); break;
+    }
+#undef DFM_GO2
+#undef DFM_GO
+    return check_launch("k_warp_cl");
+}
+
+int launch_warp_cl_bwd(const float *gout, const float *img, const float *field, float *gimg, float *gfield, int B,
+                       int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, unsigned flags,
+                       cudaStream_t st) {
+    if (!cl_ok(C, Xi, Yi, Zi) || (uint64_t)X * Y * Z * (uint64_t)C >= (1ull << 31)) return DFM_EUNSUPPORTED;
+    const uint32_t N = (uint32_t)X * Y * Z;
+    dim3 grid((N + 255) / 256, B), block(256);
+    const FastDiv zd = make_fastdiv(Z), yd = make_fastdiv(Y);
+    const int fcl = (flags & DFM_FIELD_IN_CL) ? 1 : 0, gcl = (flags & DFM_FIELD_OUT_CL) ? 1 : 0;
+#define DFM_GO(S, M, I, G) k_warp_cl_bwd<S, M, I, G><<<grid, block, 0, st>>>(gout, img, field, gimg, gfield, C, Xi, Yi, Zi, N, has_fill, fcl, gcl, zd, yd)
+#define DFM_GO2(S, M) do { if (gimg && gfield) DFM_GO(S, M, true, true); else if (gimg) DFM_GO(S, M, true, false); else DFM_GO(S, M, false, true); } while (0)
+    if (C > 32) DFM_GO2(5, true);
+    else switch (cpad_shift(C)) {
+        case 1: DFM_GO2(1, false); break;
+        case 2: DFM_GO2(2, false); break;
+        case 3: DFM_GO2(3, false); break;
+        case 4: DFM_GO2(4, false); break;
+        default: DFM_GO2(5, false); break;
+    }
+#undef DFM_GO2
+#undef DFM_GO
+    return check_launch("k_warp_cl_bwd");
+}
+
+}  // namespace dfm

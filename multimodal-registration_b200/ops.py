@@ -209,12 +209,8 @@ def warp(img, field, interp_method=LINEAR, fill_value=None, loc_absolute=False):
     if code == _lib.DFM_LINEAR:
         if img.dtype != torch.float32:
             img = img.float()
-        if img.shape[-1] > 1 and layout_of(img) != 'planar' and not loc_absolute:
-            # channels-last multi-channel image (the reference layout): one transposition pass, then the
-            # planar TMA channel-ring kernel -- faster than strided channels-last gathers even with the
-            # extra pass (the output stays planar, a permuted view with the logical channels-last shape)
-            img = to_layout(img, 'planar')
-            field = to_layout(field, 'planar')
+        # multi-channel images keep their layout: channels-last (the reference layout) runs the
+        # lanes-over-channels kernel (dfm_warp_cl.cu), planar the TMA channel ring (dfm_brick_mc.cu)
         if not loc_absolute and torch.is_grad_enabled() and (img.requires_grad or field.requires_grad):
             return _WarpLinear.apply(img, field, fill_value)
         return _warp_fwd_raw(img.detach(), field.detach(), LINEAR, fill_value, loc_absolute)

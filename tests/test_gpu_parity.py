@@ -425,6 +425,30 @@ def test_warp_backward_field_only_planar_multichannel(shape, C, std, fill):
     np.testing.assert_allclose(host(tf_.grad), gf, rtol=2e-4, atol=5e-5)
 
 
+@pytest.mark.parametrize('C', [2, 3, 5, 8, 13, 17, 26, 40])
+@pytest.mark.parametrize('field_layout,fill', [('cl', None), ('planar', 0.0)])
+def test_warp_channels_last_multichannel_fwd_bwd(C, field_layout, fill):
+    # the reference layout (lanes-over-channels kernel): every lane mapping (2..32 lanes per voxel, 32-channel
+    # chunks), a voxel count that is not a multiple of 32, forward bit-parity and both gradients
+    rng = np.random.default_rng(1000 + C)
+    shape = (5, 7, 9)
+    img = rng.random((2,) + shape + (C,))
+    field = smooth_noise(rng, (2,) + shape + (3,), 2.5).astype(np.float64)
+    g, (gi, gf) = _grads_oracle(lambda i, f: to.spatial_transformer(i, f, 'linear', fill), img, field)
+    ti = dev(img.astype(np.float32), 'cl').requires_grad_(True)
+    tf_ = dev(field.astype(np.float32), field_layout).requires_grad_(True)
+    out = ops.warp(ti, tf_, 'linear', fill)
+    assert ops.layout_of(out) == 'cl'
+    assert_linear_parity(host(out.detach()), io.spatial_transformer(img.astype(np.float32), field.astype(np.float32), 'linear', fill))
+    out.backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(ti.grad), gi, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(host(tf_.grad), gf, rtol=2e-4, atol=5e-5)
+    # d/dfield only (image without gradient): the training step's `pred` gradient
+    tf2 = dev(field.astype(np.float32), field_layout).requires_grad_(True)
+    ops.warp(dev(img.astype(np.float32), 'cl'), tf2, 'linear', fill).backward(dev(g, 'cl'))
+    np.testing.assert_allclose(host(tf2.grad), gf, rtol=2e-4, atol=5e-5)
+
+
 @pytest.mark.parametrize('nsteps', [1, 3, 5])
 def test_vecint_backward(nsteps):
     rng = np.random.default_rng(43)
