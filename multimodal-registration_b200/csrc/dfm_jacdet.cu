@@ -114,6 +114,18 @@ __device__ __forceinline__ float d4f(float m2, float m1, float p1, float p2) {
     return fmaf(8.f, p1 - m1, m2 - p2);            // 12 * derivative
 }
 
+// det(I + grad u) from J = 12 * (I + grad u) with the 12 still to be added on the diagonal:
+// 2x2 minors in fp32 with one fused rounding each, combined and scaled in fp64
+__device__ __forceinline__ double det12(float (&J)[3][3]) {
+    J[0][0] += 12.f; J[1][1] += 12.f; J[2][2] += 12.f;
+    const float m0 = fmaf(J[1][1], J[2][2], -J[1][2] * J[2][1]);
+    const float m1 = fmaf(J[1][0], J[2][2], -J[1][2] * J[2][0]);
+    const float m2 = fmaf(J[1][0], J[2][1], -J[1][1] * J[2][0]);
+    return ((double)J[0][0] * (double)m0 - (double)J[0][1] * (double)m1 + (double)J[0][2] * (double)m2) * (1.0 / 1728.0);
+}
+__device__ __forceinline__ void store_pair(float *q, double a, double b) { *reinterpret_cast<float2 *>(q) = make_float2((float)a, (float)b); }
+__device__ __forceinline__ void store_pair(double *q, double a, double b) { *reinterpret_cast<double2 *>(q) = make_double2(a, b); }
+
 // TMA plane ring: one 4-D box {JP_Z, JP_Y, 1, 3} per input plane, J_SLOTS deep, one mbarrier per
 // slot.  A slot is re-armed only after the __syncthreads() that follows its last reader.
 template <typename Tout>
@@ -132,9 +144,12 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
     const int Xo = X - 4, Yo = Y - 4, Zo = Z - 4;
     const int nxo = min(JT_X, Xo - xo0);                     // output planes of this CTA
     const int np = nxo + 4;                                  // input planes
-    const int zo = zo0 + lane;
-    const bool okz = zo < Zo;
-    const bool oky0 = (yo0 + warp) < Yo, oky1 = (yo0 + warp + 8) < Yo;
+    // a thread owns TWO z-adjacent outputs (z even) of one row: every stencil read is an aligned
+    // 8-byte shared load (LDS.64) and the z stencil shares its taps between the two outputs
+    const int row = warp * 2 + (lane >> 4), zp = (lane & 15) * 2;
+    const int zo = zo0 + zp, yo = yo0 + row;
+    const bool ok0 = yo < Yo && zo < Zo, ok1 = yo < Yo && (zo + 1) < Zo;
+    const bool pair_store = ok1 && !(Zo & 1);                // 8/16-byte aligned pair store
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -148,7 +163,7 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
     if (threadIdx.x == 0)
         for (int p = 0; p < min(np, J_SLOTS - 2); ++p) issue(p);
 
-    float win[3][2][5];
+    float win[3][2][5];                                      // [component][z / z+1][plane ring]
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -156,6 +171,9 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
 #pragma unroll
             for (int k = 0; k < 5; ++k) win[c][r][k] = 0.f;
     double s = 0.0, s2 = 0.0, nn = 0.0;
+    Tout *dp = det ? det + (size_t)blockIdx.z * Xo * Yo * Zo + ((size_t)xo0 * Yo + yo) * Zo + zo : nullptr;
+    const size_t dplane = (size_t)Yo * Zo;
+#define PL2(slot, c, y, z) (*reinterpret_cast<const float2 *>(&PL(slot, c, y, z)))
 
     // one step: plane p arrives, its centres enter the register window at position (p % 5), and if
     // p >= 4 the determinants of output plane p - 4 (centre plane p - 2) are produced.  The window is
@@ -165,31 +183,34 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
         const int slot = p % J_SLOTS;                                                                                 \
         mbar_wait(&bar[slot], (uint32_t)((p / J_SLOTS) & 1));                                                         \
         _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                               \
-            win[c][0][K] = PL(slot, c, warp + 2, lane + 2);                                                        \
-            win[c][1][K] = PL(slot, c, warp + 10, lane + 2);                                                       \
+            const float2 t = PL2(slot, c, row + 2, zp + 2);                                                           \
+            win[c][0][K] = t.x; win[c][1][K] = t.y;                                                                   \
         }                                                                                                             \
         if (p >= 4) {                                                                                                 \
-            const int xo = xo0 + p - 4, cs = (p - 2) % J_SLOTS;                                                       \
-            _Pragma("unroll") for (int r = 0; r < 2; ++r) {                                                           \
-                if (okz && (r ? oky1 : oky0)) {                                                                       \
-                    const int yy = warp + 8 * r + 2, zz = lane + 2;                                                   \
-                    float J[3][3];         /* 12 * (I + grad u): det(I + J) = det(12 I + 12 J) / 12^3 */                \
-                    _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                   \
-                        J[c][0] = d4f(win[c][r][(K + 1) % 5], win[c][r][(K + 2) % 5], win[c][r][(K + 4) % 5], win[c][r][K]); \
-                        J[c][1] = d4f(PL(cs, c, yy - 2, zz), PL(cs, c, yy - 1, zz), PL(cs, c, yy + 1, zz), PL(cs, c, yy + 2, zz)); \
-                        J[c][2] = d4f(PL(cs, c, yy, zz - 2), PL(cs, c, yy, zz - 1), PL(cs, c, yy, zz + 1), PL(cs, c, yy, zz + 2)); \
-                    }                                                                                                 \
-                    J[0][0] += 12.f; J[1][1] += 12.f; J[2][2] += 12.f;                                                \
-                    /* 2x2 minors in fp32 with one fused rounding each, combined and scaled in fp64 */                \
-                    const float m0 = fmaf(J[1][1], J[2][2], -J[1][2] * J[2][1]);                                      \
-                    const float m1 = fmaf(J[1][0], J[2][2], -J[1][2] * J[2][0]);                                      \
-                    const float m2 = fmaf(J[1][0], J[2][1], -J[1][1] * J[2][0]);                                      \
-                    const double dval = ((double)J[0][0] * (double)m0 - (double)J[0][1] * (double)m1 +                \
-                                         (double)J[0][2] * (double)m2) * (1.0 / 1728.0);                              \
-                    if (det)                                                                                          \
-                        det[(size_t)blockIdx.z * Xo * Yo * Zo + ((size_t)xo * Yo + (yo0 + warp + 8 * r)) * Zo + zo] = (Tout)dval; \
-                    s += dval; s2 += dval * dval; nn += (dval < 0.0) ? 1.0 : 0.0;                                     \
+            const int cs = (p - 2) % J_SLOTS;                                                                         \
+            if (ok0) {                                                                                                \
+                const int yy = row + 2, zz = zp + 2;                                                                  \
+                float JA[3][3], JB[3][3];  /* 12 * (I + grad u) at z and z+1: det(I + J) = det(12 I + 12 J) / 12^3 */  \
+                _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                       \
+                    const float2 ym2 = PL2(cs, c, yy - 2, zz), ym1 = PL2(cs, c, yy - 1, zz);                          \
+                    const float2 yp1 = PL2(cs, c, yy + 1, zz), yp2 = PL2(cs, c, yy + 2, zz);                          \
+                    const float2 zl = PL2(cs, c, yy, zz - 2), zh = PL2(cs, c, yy, zz + 2);                            \
+                    const float c0 = win[c][0][(K + 3) % 5], c1 = win[c][1][(K + 3) % 5];                             \
+                    JA[c][0] = d4f(win[c][0][(K + 1) % 5], win[c][0][(K + 2) % 5], win[c][0][(K + 4) % 5], win[c][0][K]); \
+                    JB[c][0] = d4f(win[c][1][(K + 1) % 5], win[c][1][(K + 2) % 5], win[c][1][(K + 4) % 5], win[c][1][K]); \
+                    JA[c][1] = d4f(ym2.x, ym1.x, yp1.x, yp2.x);                                                       \
+                    JB[c][1] = d4f(ym2.y, ym1.y, yp1.y, yp2.y);                                                       \
+                    JA[c][2] = d4f(zl.x, zl.y, c1, zh.x);                                                             \
+                    JB[c][2] = d4f(zl.y, c0, zh.x, zh.y);                                                             \
                 }                                                                                                     \
+                const double da = det12(JA), db = det12(JB);                                                          \
+                if (dp) {                                                                                             \
+                    Tout *q = dp + (size_t)(p - 4) * dplane;                                                          \
+                    if (pair_store) store_pair(q, da, db);                                                            \
+                    else { q[0] = (Tout)da; if (ok1) q[1] = (Tout)db; }                                               \
+                }                                                                                                     \
+                s += da; s2 += da * da; nn += (da < 0.0) ? 1.0 : 0.0;                                                 \
+                if (ok1) { s += db; s2 += db * db; nn += (db < 0.0) ? 1.0 : 0.0; }                                    \
             }                                                                                                         \
         }                                                                                                             \
         __syncthreads();   /* every reader of plane p - 2's predecessor slots is done */                              \
@@ -202,6 +223,7 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
         JAC_STEP(0) JAC_STEP(1) JAC_STEP(2) JAC_STEP(3) JAC_STEP(4)
     }
 #undef JAC_STEP
+#undef PL2
 #undef PL
     if (!partials) return;
 #pragma unroll
