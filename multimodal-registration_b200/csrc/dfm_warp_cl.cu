@@ -9,7 +9,7 @@
 //   phase B  lane = channel: for each of the 32 voxels the record is broadcast back (3-4 LDS.128)
 //            and every lane gathers its channel of the 8 corners; small channel counts put
 //            32 / Cpad voxels side by side in the warp, large ones loop over 32-channel chunks.
-// Backward: d/d field sums over channels with a warp reduction (no atomics); d/d img scatters
+// Backward: d/d field sums over channels through shared memory (no atomics); d/d img scatters
 // with coalesced float atomics (reference semantics: gather back-propagates as scatter-add).
 // Arithmetic per value is the shared tri_weights / tri_accumulate, so the forward pass is
 // bit-identical to the other linear kernels in both builds.
@@ -39,6 +39,17 @@ __device__ __forceinline__ void voxel_xyz(uint32_t n, FastDiv zdiv, FastDiv ydiv
     y = q - x * ydiv.d;
 }
 
+// V = 1 or 2 consecutive channels per lane (V = 2 needs an even C: every run then starts 8-byte aligned)
+template <int V> __device__ __forceinline__ void ldv(const float *p, float (&a)[V]);
+template <> __device__ __forceinline__ void ldv<1>(const float *p, float (&a)[1]) { a[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ldv<2>(const float *p, float (&a)[2]) {
+    const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    a[0] = t.x; a[1] = t.y;
+}
+template <int V> __device__ __forceinline__ void stv(float *p, const float (&a)[V]);
+template <> __device__ __forceinline__ void stv<1>(float *p, const float (&a)[1]) { *p = a[0]; }
+template <> __device__ __forceinline__ void stv<2>(float *p, const float (&a)[2]) { *reinterpret_cast<float2 *>(p) = make_float2(a[0], a[1]); }
+
 // phase A shared by forward and backward: sample location of voxel n (lane = voxel)
 __device__ __forceinline__ void load_loc(const float *__restrict__ fb, uint32_t n, uint32_t N, bool field_cl, bool absolute,
                                          FastDiv zdiv, FastDiv ydiv, float &lx, float &ly, float &lz) {
@@ -52,7 +63,7 @@ __device__ __forceinline__ void load_loc(const float *__restrict__ fb, uint32_t 
 }
 
 // CSHIFT: log2 of the lanes per voxel (Cpad >= C, or 32 with MULTI = loop over 32-channel chunks)
-template <int CSHIFT, bool MULTI, bool HF>
+template <int CSHIFT, int V, bool MULTI, bool HF>
 __global__ void __launch_bounds__(256)
 k_warp_cl(const float *__restrict__ img, const float *__restrict__ field, float *__restrict__ out, int C, int Xi,
           int Yi, int Zi, uint32_t N, float fill, int field_cl, int absolute, FastDiv zdiv, FastDiv ydiv) {
@@ -77,11 +88,10 @@ k_warp_cl(const float *__restrict__ img, const float *__restrict__ field, float 
         s_rec[warp][lane] = r;
     }
     __syncwarp();
-    // ---- phase B: lane = channel -------------------------------------------------------------
-    const int sub = lane >> CSHIFT, c0 = lane & (CPAD - 1);
-    // corner offsets kept in vector registers: address = IMAD.WIDE.U32(offset, 4, p), one instruction per load
-    const uint32_t oC = vreg((uint32_t)C), oZ = vreg((uint32_t)Zi * C), oY = vreg((uint32_t)Yi * Zi * C);
-    const uint32_t o3 = vreg(oZ + oC), o5 = vreg(oY + oC), o6 = vreg(oY + oZ), o7 = vreg(oY + oZ + oC);
+    // ---- phase B: lane = V channels ------------------------------------------------------------
+    const int sub = lane >> CSHIFT, c0 = (lane & (CPAD - 1)) * V;
+    const uint32_t oC = (uint32_t)C, oZ = (uint32_t)Zi * C, oY = (uint32_t)Yi * Zi * C;
+    const uint32_t o3 = oZ + oC, o5 = oY + oC, o6 = oY + oZ, o7 = oY + oZ + oC;
     const bool lane_on = MULTI || c0 < C;
     const uint32_t nv = min(32u, N - n0);                             // voxels of this warp (warp-uniform)
     float *po = out + (size_t)blockIdx.y * C * N + (size_t)n0 * C + (uint32_t)sub * oC + c0;
@@ -92,21 +102,19 @@ k_warp_cl(const float *__restrict__ img, const float *__restrict__ field, float 
         if ((uint32_t)j >= nv || !lane_on) continue;
         const FwdRec r = s_rec[warp][j];
         const float *p = pi + r.base;
-        if (MULTI) {
-            for (int c = c0; c < C; c += 32) {
-                const float *q = p + (c - c0);
-                const float v[8] = {__ldg(q), __ldg(q + oC), __ldg(q + oZ), __ldg(q + o3),
-                                    __ldg(q + oY), __ldg(q + o5), __ldg(q + o6), __ldg(q + o7)};
-                float a = tri_accumulate(r.w, v);
-                if (HF && r.dead) a = fill;
-                po[c - c0] = a;
+        for (int cc = 0; cc < (MULTI ? C - c0 : 1); cc += 32 * V) {
+            const float *q = p + cc;
+            float v[8][V];
+            ldv<V>(q, v[0]); ldv<V>(q + oC, v[1]); ldv<V>(q + oZ, v[2]); ldv<V>(q + o3, v[3]);
+            ldv<V>(q + oY, v[4]); ldv<V>(q + o5, v[5]); ldv<V>(q + o6, v[6]); ldv<V>(q + o7, v[7]);
+            float a[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const float t[8] = {v[0][u], v[1][u], v[2][u], v[3][u], v[4][u], v[5][u], v[6][u], v[7][u]};
+                a[u] = tri_accumulate(r.w, t);
+                if (HF && r.dead) a[u] = fill;
             }
-        } else {
-            const float v[8] = {__ldg(p), __ldg(p + oC), __ldg(p + oZ), __ldg(p + o3),
-                                __ldg(p + oY), __ldg(p + o5), __ldg(p + o6), __ldg(p + o7)};
-            float a = tri_accumulate(r.w, v);
-            if (HF && r.dead) a = fill;
-            *po = a;
+            stv<V>(po + cc, a);
         }
     }
 }
@@ -122,40 +130,16 @@ struct __align__(16) BwdRec {
     uint32_t pad[3];
 };
 
-// sum of three per-lane values over the 2^cshift lanes of a voxel; every lane of the group gets the sums
-__device__ __forceinline__ void group_sum3(float &a, float &b, float &c, int cshift) {
-    for (int o = (1 << cshift) >> 1; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-}
-// the same over the whole warp with 6 shuffles instead of 15: after two folding steps every lane
-// carries one of the three sums, three more steps finish it; lane (q << 3) holds sum q on return
-__device__ __forceinline__ float warp_sum3_folded(float a, float b, float c, int lane) {
-    const bool up16 = lane & 16, up8 = lane & 8;
-    // step 1 (xor 16): lower half keeps (a, b), upper half keeps (c, 0)
-    const float s1 = __shfl_xor_sync(0xffffffffu, up16 ? a : c, 16);
-    const float s2 = __shfl_xor_sync(0xffffffffu, up16 ? b : 0.f, 16);
-    float p = up16 ? c + s1 : a + s1;         // a (lower) | c (upper)
-    float q = up16 ? s2 : b + s2;             // b (lower) | 0 + (partner's 0) (upper)
-    // step 2 (xor 8): lanes with bit 3 clear keep p, the others keep q
-    const float s3 = __shfl_xor_sync(0xffffffffu, up8 ? p : q, 8);
-    float r = up8 ? q + s3 : p + s3;          // bits (4,3): 00 a, 01 b, 10 c, 11 0
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-
-template <int CSHIFT, bool MULTI, bool NEED_IMG, bool NEED_FIELD>
+template <int CSHIFT, int V, bool MULTI, bool NEED_IMG, bool NEED_FIELD>
 __global__ void __launch_bounds__(256)
 k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ field,
               float *__restrict__ gimg, float *__restrict__ gfield, int C, int Xi, int Yi, int Zi, uint32_t N,
               int has_fill, int field_cl, int gfield_cl, FastDiv zdiv, FastDiv ydiv) {
+    constexpr int CPAD = 1 << CSHIFT, VPW = 32 >> CSHIFT;
+    constexpr int CV = VPW > 8 ? VPW : (CSHIFT == 5 ? 4 : 8), RL = CPAD + 1;          // reduction chunk (voxels), row pitch
     __shared__ BwdRec s_rec[8][32];
     __shared__ __align__(16) float s_w[NEED_IMG ? 8 : 1][32][8];
-    constexpr int CPAD = 1 << CSHIFT, VPW = 32 >> CSHIFT;
+    __shared__ float s_red[NEED_FIELD ? 8 : 1][3 * CV * RL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n0 = blockIdx.x * 256u + warp * 32u;
     if (n0 >= N) return;
@@ -194,34 +178,40 @@ k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, con
         }
     }
     __syncwarp();
-    const int sub = lane >> CSHIFT, c0 = lane & (CPAD - 1);
+    const int sub = lane >> CSHIFT, c0 = (lane & (CPAD - 1)) * V;
     const uint32_t oC = (uint32_t)C, oZ = (uint32_t)Zi * C, oY = (uint32_t)Yi * Zi * C;
     const uint32_t o3 = oZ + oC, o5 = oY + oC, o6 = oY + oZ, o7 = oY + oZ + oC;
     const bool lane_on = MULTI || c0 < C;
+    const int nl = min(CPAD, (C + V - 1) / V);                        // lanes of a voxel that carry channels
     const uint32_t nv = min(32u, N - n0);
     const float *pg = gout + (size_t)blockIdx.y * C * N + (size_t)n0 * C + (uint32_t)sub * oC + c0;
     const float *pi = img + (size_t)blockIdx.y * C * Ni + c0;
     float *pq = NEED_IMG ? gimg + (size_t)blockIdx.y * C * Ni + c0 : nullptr;
     float mine[3] = {0.f, 0.f, 0.f};                       // gradient of voxel n0 + lane
-#pragma unroll 2
+#pragma unroll 4
     for (int j0 = 0; j0 < 32; j0 += VPW, pg += VPW * oC) {
         const int j = j0 + sub;
         float sx = 0.f, sy = 0.f, sz = 0.f;
         if ((uint32_t)j < nv && lane_on) {
             const BwdRec r = s_rec[warp][j];
-            for (int cc = 0; cc < (MULTI ? C - c0 : 1); cc += 32) {
-                const float g = __ldg(pg + cc);
+            for (int cc = 0; cc < (MULTI ? C - c0 : 1); cc += 32 * V) {
+                float g[V];
+                ldv<V>(pg + cc, g);
                 if (NEED_FIELD) {
                     const float *p = pi + r.base + cc;
-                    const float v[8] = {__ldg(p), __ldg(p + oC), __ldg(p + oZ), __ldg(p + o3),
-                                        __ldg(p + oY), __ldg(p + o5), __ldg(p + o6), __ldg(p + o7)};
-                    float dx = r.dx[0] * (v[4] - v[0]);
-                    dx = fmaf(r.dx[1], v[5] - v[1], dx); dx = fmaf(r.dx[2], v[6] - v[2], dx); dx = fmaf(r.dx[3], v[7] - v[3], dx);
-                    float dy = r.dy[0] * (v[2] - v[0]);
-                    dy = fmaf(r.dy[1], v[3] - v[1], dy); dy = fmaf(r.dy[2], v[6] - v[4], dy); dy = fmaf(r.dy[3], v[7] - v[5], dy);
-                    float dz = r.dz[0] * (v[1] - v[0]);
-                    dz = fmaf(r.dz[1], v[3] - v[2], dz); dz = fmaf(r.dz[2], v[5] - v[4], dz); dz = fmaf(r.dz[3], v[7] - v[6], dz);
-                    sx = fmaf(g, dx, sx); sy = fmaf(g, dy, sy); sz = fmaf(g, dz, sz);
+                    float v[8][V];
+                    ldv<V>(p, v[0]); ldv<V>(p + oC, v[1]); ldv<V>(p + oZ, v[2]); ldv<V>(p + o3, v[3]);
+                    ldv<V>(p + oY, v[4]); ldv<V>(p + o5, v[5]); ldv<V>(p + o6, v[6]); ldv<V>(p + o7, v[7]);
+#pragma unroll
+                    for (int u = 0; u < V; ++u) {
+                        float dx = r.dx[0] * (v[4][u] - v[0][u]);
+                        dx = fmaf(r.dx[1], v[5][u] - v[1][u], dx); dx = fmaf(r.dx[2], v[6][u] - v[2][u], dx); dx = fmaf(r.dx[3], v[7][u] - v[3][u], dx);
+                        float dy = r.dy[0] * (v[2][u] - v[0][u]);
+                        dy = fmaf(r.dy[1], v[3][u] - v[1][u], dy); dy = fmaf(r.dy[2], v[6][u] - v[4][u], dy); dy = fmaf(r.dy[3], v[7][u] - v[5][u], dy);
+                        float dz = r.dz[0] * (v[1][u] - v[0][u]);
+                        dz = fmaf(r.dz[1], v[3][u] - v[2][u], dz); dz = fmaf(r.dz[2], v[5][u] - v[4][u], dz); dz = fmaf(r.dz[3], v[7][u] - v[6][u], dz);
+                        sx = fmaf(g[u], dx, sx); sy = fmaf(g[u], dy, sy); sz = fmaf(g[u], dz, sz);
+                    }
                 }
                 if (NEED_IMG) {
                     float *q = pq + r.base + cc;
@@ -230,25 +220,34 @@ k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, con
                     const uint32_t off[8] = {0u, oC, oZ, o3, oY, o5, o6, o7};
                     const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float a = w[k] * g;
-                        if (a != 0.f) atomicAdd(q + off[k], a);
-                    }
+                    for (int k = 0; k < 8; ++k)
+#pragma unroll
+                        for (int u = 0; u < V; ++u) {
+                            const float a = w[k] * g[u];
+                            if (a != 0.f) atomicAdd(q + off[k] + u, a);
+                        }
                 }
             }
         }
         if (NEED_FIELD) {
-            if (CSHIFT == 5) {
-                const float s = warp_sum3_folded(sx, sy, sz, lane);          // lane 0: x, 8: y, 16: z
-                const float tx = __shfl_sync(0xffffffffu, s, 0), ty = __shfl_sync(0xffffffffu, s, 8),
-                            tz = __shfl_sync(0xffffffffu, s, 16);
-                if (lane == j0) { mine[0] = tx; mine[1] = ty; mine[2] = tz; }
-            } else {
-                group_sum3(sx, sy, sz, CSHIFT);
-                const int src = ((lane - j0) & (VPW - 1)) << CSHIFT;       // group of voxel j0 + (lane - j0)
-                const float tx = __shfl_sync(0xffffffffu, sx, src), ty = __shfl_sync(0xffffffffu, sy, src),
-                            tz = __shfl_sync(0xffffffffu, sz, src);
-                if (lane >= j0 && lane < j0 + VPW) { mine[0] = tx; mine[1] = ty; mine[2] = tz; }
+            // channel sum through shared memory: each lane parks its partial sums in the row of its
+            // voxel; after a chunk of CV voxels the lanes owning those voxels add up their rows
+            // (odd row pitch: conflict-free both ways) -- about 4 instructions per voxel, no shuffles
+            const int jj = j & (CV - 1);
+            if ((uint32_t)j < nv && lane_on) {
+                float *rr = &s_red[warp][jj * RL + (lane & (CPAD - 1))];
+                rr[0] = sx; rr[CV * RL] = sy; rr[2 * CV * RL] = sz;
+            }
+            if (((j0 + VPW) & (CV - 1)) == 0) {                        // chunk complete (compile-time after unrolling)
+                __syncwarp();
+                const int base = j0 + VPW - CV;
+                if (lane >= base && lane < base + CV) {
+                    const float *rr = &s_red[warp][(lane - base) * RL];
+                    float ax = 0.f, ay = 0.f, az = 0.f;
+                    for (int i = 0; i < nl; ++i) { ax += rr[i]; ay += rr[CV * RL + i]; az += rr[2 * CV * RL + i]; }
+                    mine[0] = ax; mine[1] = ay; mine[2] = az;
+                }
+                __syncwarp();
             }
         }
     }
@@ -272,6 +271,7 @@ static int cpad_shift(int C) {
     while ((1 << s) < C && s < 5) ++s;
     return s;
 }
+static bool aligned8(const void *p) { return ((uintptr_t)p & 7u) == 0; }
 
 int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
                        int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
@@ -280,16 +280,22 @@ int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, 
     dim3 grid((N + 255) / 256, B), block(256);
     const FastDiv zd = make_fastdiv(Z), yd = make_fastdiv(Y);
     const int fcl = (flags & DFM_FIELD_IN_CL) ? 1 : 0, ab = (flags & DFM_LOC_ABSOLUTE) ? 1 : 0;
-#define DFM_GO(S, M, H) k_warp_cl<S, M, H><<<grid, block, 0, st>>>(img, field, out, C, Xi, Yi, Zi, N, fill, fcl, ab, zd, yd)
-#define DFM_GO2(S, M) do { if (has_fill) DFM_GO(S, M, true); else DFM_GO(S, M, false); } while (0)
-    if (C > 32) DFM_GO2(5, true);
-    else switch (cpad_shift(C)) {
-        case 1: DFM_GO2(1, false); break;
-        case 2: DFM_GO2(2, false); break;
-        case 3: DFM_GO2(3, false); break;
-        case 4: DFM_GO2(4, false); break;
-        default: DFM_GO2(5, false); break;
+    static const bool no_v2 = getenv("DFM_CL_NO_V2") != nullptr;      // tuning aid
+    const bool v2 = !no_v2 && C >= 4 && C % 2 == 0 && aligned8(img) && aligned8(out);
+    const int lanes = v2 ? C / 2 : C;                                 // lanes a voxel needs
+#define DFM_GO(S, V, M, H) k_warp_cl<S, V, M, H><<<grid, block, 0, st>>>(img, field, out, C, Xi, Yi, Zi, N, fill, fcl, ab, zd, yd)
+#define DFM_GO2(S, V, M) do { if (has_fill) DFM_GO(S, V, M, true); else DFM_GO(S, V, M, false); } while (0)
+#define DFM_GO3(V)                                      \
+    if (lanes > 32) DFM_GO2(5, V, true);                \
+    else switch (cpad_shift(lanes)) {                   \
+        case 0: case 1: DFM_GO2(1, V, false); break;    \
+        case 2: DFM_GO2(2, V, false); break;            \
+        case 3: DFM_GO2(3, V, false); break;            \
+        case 4: DFM_GO2(4, V, false); break;            \
+        default: DFM_GO2(5, V, false); break;           \
     }
+    if (v2) { DFM_GO3(2) } else { DFM_GO3(1) }
+#undef DFM_GO3
 #undef DFM_GO2
 #undef DFM_GO
     return check_launch("k_warp_cl");
@@ -303,16 +309,22 @@ int launch_warp_cl_bwd(const float *gout, const float *img, const float *field, 
     dim3 grid((N + 255) / 256, B), block(256);
     const FastDiv zd = make_fastdiv(Z), yd = make_fastdiv(Y);
     const int fcl = (flags & DFM_FIELD_IN_CL) ? 1 : 0, gcl = (flags & DFM_FIELD_OUT_CL) ? 1 : 0;
-#define DFM_GO(S, M, I, G) k_warp_cl_bwd<S, M, I, G><<<grid, block, 0, st>>>(gout, img, field, gimg, gfield, C, Xi, Yi, Zi, N, has_fill, fcl, gcl, zd, yd)
-#define DFM_GO2(S, M) do { if (gimg && gfield) DFM_GO(S, M, true, true); else if (gimg) DFM_GO(S, M, true, false); else DFM_GO(S, M, false, true); } while (0)
-    if (C > 32) DFM_GO2(5, true);
-    else switch (cpad_shift(C)) {
-        case 1: DFM_GO2(1, false); break;
-        case 2: DFM_GO2(2, false); break;
-        case 3: DFM_GO2(3, false); break;
-        case 4: DFM_GO2(4, false); break;
-        default: DFM_GO2(5, false); break;
+    static const bool no_v2 = getenv("DFM_CL_NO_V2") != nullptr;      // tuning aid
+    const bool v2 = !no_v2 && C >= 4 && C % 2 == 0 && aligned8(img) && aligned8(gout) && aligned8(gimg);
+    const int lanes = v2 ? C / 2 : C;
+#define DFM_GO(S, V, M, I, G) k_warp_cl_bwd<S, V, M, I, G><<<grid, block, 0, st>>>(gout, img, field, gimg, gfield, C, Xi, Yi, Zi, N, has_fill, fcl, gcl, zd, yd)
+#define DFM_GO2(S, V, M) do { if (gimg && gfield) DFM_GO(S, V, M, true, true); else if (gimg) DFM_GO(S, V, M, true, false); else DFM_GO(S, V, M, false, true); } while (0)
+#define DFM_GO3(V)                                      \
+    if (lanes > 32) DFM_GO2(5, V, true);                \
+    else switch (cpad_shift(lanes)) {                   \
+        case 0: case 1: DFM_GO2(1, V, false); break;    \
+        case 2: DFM_GO2(2, V, false); break;            \
+        case 3: DFM_GO2(3, V, false); break;            \
+        case 4: DFM_GO2(4, V, false); break;            \
+        default: DFM_GO2(5, V, false); break;           \
     }
+    if (v2) { DFM_GO3(2) } else { DFM_GO3(1) }
+#undef DFM_GO3
 #undef DFM_GO2
 #undef DFM_GO
     return check_launch("k_warp_cl_bwd");
