@@ -283,7 +283,7 @@ def run_own(args):
         dom_name = max(kernels, key=lambda n: kernels[n]['share_of_step'])
         dom = kernels[dom_name]
         cores = os.cpu_count() or 1
-        n_cpu = 2
+        n_cpu = 24                                   # ~0.55 s per pair on 16 host threads -> 10-15 s of CPU work
         cpu_s = float('nan') if args.no_e2e else cpu_pipeline_seconds(n_cpu)
         line = {
             'metric': METRIC, 'value': voxels / (ms_per_step * 1e-3), 'unit': UNIT, 'n_gpus': world,
@@ -319,9 +319,9 @@ def run_own(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch PER VOLUME PAIR, from the committed
 # `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
 TRAFFIC_NCU_PER_PAIR = {
-    'ss_step(k_ss_brick)': (59.004e6 + 22.844e6) / 8,
-    'rescale_x2(k_upsample3_march)': (59.011e6 + 414.804e6) / 8,
-    'warp_linear(k_warp_brick)': (629.045e6 + 143.886e6) / 8,
+    'ss_step(k_ss_brick)': (59.009e6 + 22.881e6) / 8,
+    'rescale_x2(k_upsample3_march)': (62.914e6 + 415.857e6) / 8,
+    'warp_linear(k_warp_brick)': (629.046e6 + 143.723e6) / 8,
 }
 
 
