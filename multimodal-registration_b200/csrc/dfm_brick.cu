@@ -563,6 +563,8 @@ int launch_warp_brick(const float *img, const float *field, float *out, int B, i
         case 2: return launch_warp_brick_t<8, 16, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 3: return launch_warp_brick_t<4, 10, 18, 72>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 4: return launch_warp_brick_t<8, 14, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 5: return launch_warp_brick_t<4, 8, 12, 40>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        case 6: return launch_warp_brick_t<4, 8, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
     }
 }
