@@ -182,6 +182,25 @@ def test_vecint(shape, nsteps, layout):
         assert_linear_parity(got, want)
 
 
+@pytest.mark.parametrize('save_steps', [False, True])
+def test_vecint_static_halo_per_item_bounds(save_steps):
+    # the brick kernel picks its static-halo path per batch item from a bound measured on the device:
+    # items whose displacements stay below one voxel for every step, cross the 1- and 2-voxel halos
+    # midway, or exceed them from the start must all match the oracle
+    rng = np.random.default_rng(123)
+    shape = (12, 16, 36)                                     # Z multiple of 4 (TMA path), tiles with edges
+    base = smooth_noise(rng, (4,) + shape + (3,), 1.0)
+    base /= np.abs(base).max(axis=(1, 2, 3, 4), keepdims=True)
+    svf = base * np.array([0.4, 3.0, 9.0, 60.0], np.float32).reshape(4, 1, 1, 1, 1)
+    want = io.vec_int(svf, 7)
+    t = dev(svf, 'cl')
+    if save_steps:
+        got = host(ops.vecint(t.requires_grad_(True), 7).detach())
+    else:
+        got = host(ops.vecint(t, 7))
+    assert_linear_parity(got, want)
+
+
 def test_vecint_constant_svf_known_answer():
     c = np.broadcast_to(np.array([1.5, -0.75, 0.25], np.float32), (1, 8, 8, 8, 3)).copy()
     np.testing.assert_array_equal(host(ops.vecint(dev(c), 7)), c)
