@@ -108,7 +108,7 @@ k_jacdet_finalize(const double *__restrict__ partials, double *__restrict__ stat
 // the first row, the fold test and the moments are fp64.  (The all-fp64 kernel above needs 36 fp32->fp64 conversions
 // per voxel, which run at 1/8 rate; it is kept for fp64 inputs and channels-last fields.)
 // ---------------------------------------------------------------------------------------
-constexpr int JT_X = 32, JT_Y = 16, JT_Z = 32, JP_Y = JT_Y + 4, JP_Z = JT_Z + 4, J_SLOTS = 5;
+constexpr int JT_X = 64, JT_Y = 16, JT_Z = 32, JP_Y = JT_Y + 4, JP_Z = JT_Z + 4, J_SLOTS = 5;
 
 __device__ __forceinline__ float d4f(float m2, float m1, float p1, float p2) {
     return fmaf(8.f, p1 - m1, m2 - p2);            // 12 * derivative
