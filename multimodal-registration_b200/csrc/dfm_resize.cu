@@ -435,47 +435,57 @@ static int launch_resize3_smem(const float *in, float *out, const float *cx, con
 // ---------------------------------------------------------------------------------------
 // KZ = compile-time z tap count (row length of zw): the z taps of a row are loaded together
 // (memory-level parallelism); rows shorter than KZ are zero-padded by the host tables.
-template <int KZ>
+// A thread owns RX consecutive input planes of one (y, z).  All tap loops have compile-time bounds
+// (K = the largest tap count; the host tables are zero-padded, indices are clamped), so every load of a
+// thread is independent of every other and the compiler issues them together -- the first version
+// (data-dependent loop bounds, one output per thread) was bound by its three-deep dependent chain
+// table -> gout -> store.
+template <int K, int RX>
 __global__ void __launch_bounds__(256)
 k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const int *__restrict__ xlo,
-             const int *__restrict__ xcnt, const float *__restrict__ xw, int kx, const int *__restrict__ ylo,
-             const int *__restrict__ ycnt, const float *__restrict__ yw, int ky, const int *__restrict__ zlo,
-             const float *__restrict__ zw, int Xi, int Yi, int Zi, int Xo,
+             const float *__restrict__ xw, int kx, const int *__restrict__ ylo, const float *__restrict__ yw, int ky,
+             const int *__restrict__ zlo, const float *__restrict__ zw, int kz, int Xi, int Yi, int Zi, int Xo,
              int Yo, int Zo, float s, FastDiv zdiv, uint32_t plane_items) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= plane_items) return;
     const uint32_t iy = fast_div(p, zdiv);
     const uint32_t iz = p - iy * zdiv.d;
-    const uint32_t ix = blockIdx.y;
+    const uint32_t ix0 = blockIdx.y * RX;
     const uint32_t bc = blockIdx.z;   // b*C + c
     const size_t No = (size_t)Xo * Yo * Zo, Ni = (size_t)Xi * Yi * Zi;
     const float *gb = gout + (size_t)bc * No;
-    const int x0 = __ldg(xlo + ix), nx = __ldg(xcnt + ix), y0 = __ldg(ylo + iy), ny = __ldg(ycnt + iy);
-    const int z0 = __ldg(zlo + iz);
-    float wz[KZ];
-    int oz[KZ];
+    const int y0 = __ldg(ylo + iy), z0 = __ldg(zlo + iz);
+    float wy[K], wz[K];
+    uint32_t oy[K], oz[K];
 #pragma unroll
-    for (int c = 0; c < KZ; ++c) {
-        wz[c] = __ldg(zw + iz * KZ + c);
-        oz[c] = min(z0 + c, Zo - 1);                 // padded taps have weight 0: any valid address
+    for (int c = 0; c < K; ++c) {                     // taps past the table width have weight 0 and a valid address
+        wz[c] = c < kz ? __ldg(zw + iz * kz + c) : 0.f;
+        oz[c] = (uint32_t)min(z0 + c, Zo - 1);
+        wy[c] = c < ky ? __ldg(yw + iy * ky + c) : 0.f;
+        oy[c] = (uint32_t)min(y0 + c, Yo - 1) * (uint32_t)Zo;
     }
-    float acc = 0.f;
-    for (int a = 0; a < nx; ++a) {
-        const float wx = __ldg(xw + ix * kx + a);
-        float accy = 0.f;
-        for (int b = 0; b < ny; ++b) {
-            const float *row = gb + ((size_t)(x0 + a) * Yo + (y0 + b)) * Zo;
-            float v[KZ];
 #pragma unroll
-            for (int c = 0; c < KZ; ++c) v[c] = __ldg(row + oz[c]);
-            float accz = 0.f;
+    for (int r = 0; r < RX; ++r) {
+        const uint32_t ix = ix0 + r;
+        if (ix >= (uint32_t)Xi) break;
+        const int x0 = __ldg(xlo + ix);
+        float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < KZ; ++c) accz = fmaf(wz[c], v[c], accz);
-            accy = fmaf(__ldg(yw + iy * ky + b), accz, accy);
+        for (int a = 0; a < K; ++a) {
+            const float wx = a < kx ? __ldg(xw + ix * kx + a) : 0.f;
+            const float *pl = gb + (size_t)min(x0 + a, Xo - 1) * Yo * Zo;
+            float accy = 0.f;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                float accz = 0.f;
+#pragma unroll
+                for (int c = 0; c < K; ++c) accz = fmaf(wz[c], __ldg(pl + oy[b] + oz[c]), accz);
+                accy = fmaf(wy[b], accz, accy);
+            }
+            acc = fmaf(wx, accy, acc);
         }
-        acc = fmaf(wx, accy, acc);
+        gin[(size_t)bc * Ni + ((size_t)ix * Yi + iy) * Zi + iz] = s * acc;
     }
-    gin[(size_t)bc * Ni + ((size_t)ix * Yi + iy) * Zi + iz] = s * acc;
 }
 
 }  // namespace dfm
@@ -523,23 +533,28 @@ extern "C" int dfm_resize_bwd(const float *gout, float *gin, const int *xlo, con
     if (B == 0) return DFM_OK;
     DFM_REQUIRE(gout && gin && xlo && xcnt && xw && ylo && ycnt && yw && zlo && zcnt && zw, DFM_EINVAL,
                 "dfm_resize_bwd: null pointer");
-    (void)zcnt;   // rows of zw are zero-padded to kz taps, so the z count is not needed on the device
+    (void)xcnt; (void)ycnt; (void)zcnt;   // table rows are zero-padded to k taps, so the counts are not needed on the device
     const uint32_t plane = (uint32_t)Yi * Zi;
-    dim3 grid((plane + 255) / 256, Xi, B * C), block(256);
+    const int K = kx > ky ? (kx > kz ? kx : kz) : (ky > kz ? ky : kz);
     cudaStream_t st = (cudaStream_t)stream;
     const FastDiv fd = make_fastdiv(Zi);
     const float sc = pre * post;
-#define DFM_GO(K) k_resize_bwd<K><<<grid, block, 0, st>>>(gout, gin, xlo, xcnt, xw, kx, ylo, ycnt, yw, ky, zlo, zw, Xi, Yi, Zi, Xo, Yo, Zo, sc, fd, plane)
-    switch (kz) {
-        case 1: DFM_GO(1); break;
-        case 2: DFM_GO(2); break;
-        case 3: DFM_GO(3); break;
-        case 4: DFM_GO(4); break;
-        case 5: DFM_GO(5); break;
-        case 6: DFM_GO(6); break;
-        case 7: DFM_GO(7); break;
-        case 8: DFM_GO(8); break;
-        default: return fail(DFM_EUNSUPPORTED, "dfm_resize_bwd: %d z taps per input sample (max 8: zoom factors up to ~4)", kz);
+#define DFM_GO(KK, RX)                                                                                              \
+    do {                                                                                                            \
+        dim3 grid((plane + 255) / 256, (Xi + RX - 1) / RX, B * C), block(256);                                      \
+        k_resize_bwd<KK, RX><<<grid, block, 0, st>>>(gout, gin, xlo, xw, kx, ylo, yw, ky, zlo, zw, kz, Xi, Yi, Zi, Xo, Yo, \
+                                                     Zo, sc, fd, plane);                                            \
+    } while (0)
+    switch (K) {
+        case 1: DFM_GO(1, 4); break;
+        case 2: DFM_GO(2, 4); break;
+        case 3: DFM_GO(3, 2); break;
+        case 4: DFM_GO(4, 1); break;
+        case 5: DFM_GO(5, 1); break;
+        case 6: DFM_GO(6, 1); break;
+        case 7: DFM_GO(7, 1); break;
+        case 8: DFM_GO(8, 1); break;
+        default: return fail(DFM_EUNSUPPORTED, "dfm_resize_bwd: %d taps per input sample (max 8: zoom factors up to ~4)", K);
     }
 #undef DFM_GO
     return check_launch("dfm_resize_bwd");
