@@ -293,7 +293,7 @@ def run_own(args):
             'e2e': {'value': voxels / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': int(svf_pin.numel() * 4 + img_pin.numel() * 4),
                     'd2h_bytes_per_step': int(img_pin.numel() * 4),
-                    'note': 'chunked 3-stream pipeline (batch_size 4); the second output (pre-integration flow) is the '
+                    'note': 'chunked 3-stream pipeline (batch_size 2); the second output (pre-integration flow) is the '
                             'untouched input and is returned from the host copy, not re-downloaded',
                     'api': 'voxelmorph.networks.VxmDense(...).predict_deform([source, flow]) on pinned host arrays'},
             'gpu_launches': args.steps * (INT_STEPS + 2),

@@ -131,7 +131,7 @@ struct __align__(16) BwdRec {
 };
 
 template <int CSHIFT, int V, bool MULTI, bool NEED_IMG, bool NEED_FIELD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NEED_IMG || MULTI) ? 1 : 6)
 k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ field,
               float *__restrict__ gimg, float *__restrict__ gfield, int C, int Xi, int Yi, int Zi, uint32_t N,
               int has_fill, int field_cl, int gfield_cl, FastDiv zdiv, FastDiv ydiv) {

@@ -148,7 +148,7 @@ class VxmDense(torch.nn.Module):
         return [_host.to_host(t, tag='out%d' % i, copy=copy) for i, t in enumerate(self.forward(inputs))]
 
     @torch.no_grad()
-    def predict_deform(self, inputs, copy=True, batch_size=4):
+    def predict_deform(self, inputs, copy=True, batch_size=2):
         """Keras-style (numpy in / numpy out) call of the deformation tail.
 
         Host inputs are processed in chunks of ``batch_size`` items on three CUDA streams (H2D copy,
