@@ -232,6 +232,11 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
 // =========================================================================================
 // one-channel image warp (linear)
 // =========================================================================================
+// FMODE 3 = the same fusion evaluated SEPARABLY (default build): the tile's coarse box arrives by one TMA
+// load issued at kernel start; a thread reduces each coarse plane it crosses once to its (y,z)-bilinear
+// value (4 taps x 3 components, weights fixed per thread and carrying the vector scale) and every voxel of
+// its x walk is one lerp between two held planes -- ~25 instructions per voxel instead of ~90, 11.5 KB of
+// shared memory instead of a float4 box.  Differs from the reference summation order by a few ulp.
 // FMODE: 0 = planar field, 1 = channels-last field, 2 = FUSED RescaleTransform: `field` is the
 // coarse planar field [B][3][Xh][Yh][Zh]; the displacement of every output voxel is resampled on
 // the fly from a shared-memory copy of the coarse box the tile touches (same arithmetic as
@@ -244,9 +249,12 @@ struct UpsampleArgs {
     int cap;                        // capacity (float4) of the coarse box in shared memory
 };
 
+// coarse box of FMODE 3 (TMA, one box per CTA): covers the 4 x 8 x 32 tile for zoom factors >= 2
+constexpr int HBX = 5, HBY = 8, HBZ = 24, HCS = HBX * HBY * HBZ;
+
 template <int TX, int BX, int BY, int BZ, int FMODE, bool HF>
 __global__ void __launch_bounds__(256)
-k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ img,
+k_warp_brick(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_h, const float *__restrict__ img,
              const float *__restrict__ field, float *__restrict__ out, int Xi, int Yi, int Zi, int X, int Y,
              int Z, float fill, FastDiv nzt, UpsampleArgs up) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -279,7 +287,48 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__
     __syncthreads();
 
     float l[3][TX];                                   // displacements, then CLIPPED sample locations
-    if (FMODE == 2) {
+    if (FMODE == 3) {
+        __shared__ __align__(8) uint64_t bar_h;
+        float *hbox = brick + CS;                     // [3][HBX][HBY][HBZ]
+        const int Xh = up.Xh, Yh = up.Yh, Zh = up.Zh;
+        const float hxf = (float)(Xh - 1), hyf = (float)(Yh - 1), hzf = (float)(Zh - 1);
+        // coarse box origin of this tile (tables are non-decreasing); z origin 16-byte aligned for TMA
+        const int bx0 = axis_fast_i1(__ldg(up.cx + x0), hxf, Xh - 1) - 1;
+        const int by0 = axis_fast_i1(__ldg(up.cy + yt * TY), hyf, Yh - 1) - 1;
+        const int bz0 = (axis_fast_i1(__ldg(up.cz + zt * TZ), hzf, Zh - 1) - 1) & ~3;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar_h, 1);
+            mbar_expect_tx(&bar_h, (uint32_t)(3 * HCS * sizeof(float)));
+            tma_load_4d(hbox, &tmap_h, &bar_h, bz0, by0, bx0, (int)blockIdx.z * 3);
+        }
+        const AxisF ay = axis_fast(__ldg(up.cy + yc), hyf, Yh - 1);
+        const AxisF az = axis_fast(__ldg(up.cz + zc), hzf, Zh - 1);
+        const float w4[4] = {up.pre * ay.w0 * az.w0, up.pre * ay.w0 * az.w1, up.pre * ay.w1 * az.w0, up.pre * ay.w1 * az.w1};
+        const float *h0 = hbox + (ay.i1 - 1 - by0) * HBZ + (az.i1 - 1 - bz0);
+        AxisF axs[TX];
+#pragma unroll
+        for (int i = 0; i < TX; ++i) axs[i] = axis_fast(__ldg(up.cx + x0 + min(i, nx - 1)), hxf, Xh - 1);
+        __syncthreads();                              // bar_h initialised
+        mbar_wait(&bar_h, 0);
+        float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+        int have = -1;                                // relative index of the coarse plane held in `hi`
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            const int need = axs[i].i1 - bx0;         // relative index of the upper coarse plane (CTA-uniform)
+            while (have < need) {
+                ++have;
+                const float *q = h0 + have * (HBY * HBZ);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = hi[c];
+                    const float *qc = q + c * HCS;
+                    hi[c] = fmaf(w4[3], qc[HBZ + 1], fmaf(w4[2], qc[HBZ], fmaf(w4[1], qc[1], w4[0] * qc[0])));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) l[c][i] = fmaf(axs[i].w1, hi[c], axs[i].w0 * lo[c]);
+        }
+    } else if (FMODE == 2) {
         float4 *hbox = reinterpret_cast<float4 *>(smem_raw + (size_t)CS * sizeof(float));
         const int Xh = up.Xh, Yh = up.Yh, Zh = up.Zh;
         const uint32_t Nh = (uint32_t)Xh * Yh * Zh;
@@ -504,7 +553,7 @@ static int launch_warp_brick_t(const float *img, const float *field, float *out,
     dim3 grid(nzt * nyt, nxt, B), block(256);
     const FastDiv nz = make_fastdiv(nzt);
     UpsampleArgs none = {};
-#define DFM_WB(FM, HFv) k_warp_brick<TX, BX, BY, BZ, FM, HFv><<<grid, block, smem, st>>>(tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, fill, nz, none)
+#define DFM_WB(FM, HFv) k_warp_brick<TX, BX, BY, BZ, FM, HFv><<<grid, block, smem, st>>>(tmap, tmap, img, field, out, Xi, Yi, Zi, X, Y, Z, fill, nz, none)
     if (flags & DFM_FIELD_IN_CL) {
         if (has_fill) DFM_WB(1, true); else DFM_WB(1, false);
     } else {
@@ -525,22 +574,49 @@ static int launch_rescale_warp_t(const float *img, const float *half, float *out
         const double ratio = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
         return (int)(tile * ratio) + 3;
     };
+    const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    const FastDiv nz = make_fastdiv(nzt);
+#if !DFM_EXACT_ORDER
+    // default build: separable evaluation from a TMA-staged coarse box (FMODE 3) when the box covers the tile
+    static const bool no_sep = getenv("DFM_NO_FUSED_SEP") != nullptr;                    // tuning aid
+    if (!no_sep && ext(TX, Xh, X) <= HBX && ext(TY, Yh, Y) <= HBY && ext(TZ, Zh, Z) + 3 <= HBZ &&
+        tma_source_ok(half, Xh, Yh, Zh)) {
+        CUtensorMap tmap_h;
+        if (!encode_map(&tmap_h, half, B * 3, Xh, Yh, Zh, HBX, HBY, HBZ, 3)) return DFM_EUNSUPPORTED;
+        UpsampleArgs up = {cx, cy, cz, Xh, Yh, Zh, pre, 0};
+        constexpr size_t smem = ((size_t)BX * BY * BZ + 3 * HCS) * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick(fused) smem attribute: %s", cudaGetErrorString(e));
+            const int carve = getenv("DFM_WARP_CARVEOUT") ? atoi(getenv("DFM_WARP_CARVEOUT")) : 80;   // see launch_warp_brick_t
+            cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            configured = true;
+        }
+        if (has_fill)
+            k_warp_brick<TX, BX, BY, BZ, 3, true><<<grid, block, smem, st>>>(tmap, tmap_h, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, nz, up);
+        else
+            k_warp_brick<TX, BX, BY, BZ, 3, false><<<grid, block, smem, st>>>(tmap, tmap_h, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, nz, up);
+        return check_launch("k_warp_brick(fused rescale, separable)");
+    }
+#endif
     UpsampleArgs up = {cx, cy, cz, Xh, Yh, Zh, pre, ext(TX, Xh, X) * ext(TY, Yh, Y) * ext(TZ, Zh, Z)};
     const size_t smem = (size_t)BX * BY * BZ * sizeof(float) + (size_t)up.cap * sizeof(float4);
     if (smem > 200 * 1024) return DFM_EUNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured2 = 0;
+    if (smem > configured2) {
         cudaError_t e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_brick<TX, BX, BY, BZ, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick(fused) smem attribute: %s", cudaGetErrorString(e));
-        configured = smem;
+        configured2 = smem;
     }
-    const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
-    dim3 grid(nzt * nyt, nxt, B), block(256);
     if (has_fill)
-        k_warp_brick<TX, BX, BY, BZ, 2, true><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, make_fastdiv(nzt), up);
+        k_warp_brick<TX, BX, BY, BZ, 2, true><<<grid, block, smem, st>>>(tmap, tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, nz, up);
     else
-        k_warp_brick<TX, BX, BY, BZ, 2, false><<<grid, block, smem, st>>>(tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, make_fastdiv(nzt), up);
+        k_warp_brick<TX, BX, BY, BZ, 2, false><<<grid, block, smem, st>>>(tmap, tmap, img, half, out, Xi, Yi, Zi, X, Y, Z, fill, nz, up);
     return check_launch("k_warp_brick(fused rescale)");
 }
 
@@ -548,8 +624,12 @@ int launch_rescale_warp(const float *img, const float *half, float *out, const f
                         const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
                         float pre, int has_fill, float fill, cudaStream_t st) {
     if (!tma_source_ok(img, Xi, Yi, Zi) || Xh < 2 || Yh < 2 || Zh < 2) return DFM_EUNSUPPORTED;
-    return launch_rescale_warp_t<4, 10, 16, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre,
-                                                 has_fill, fill, st);
+    static const int cfg = getenv("DFM_FUSED_CFG") ? atoi(getenv("DFM_FUSED_CFG")) : 0;     // tuning aid
+    switch (cfg) {
+        case 1: return launch_rescale_warp_t<4, 8, 14, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
+        case 2: return launch_rescale_warp_t<4, 8, 12, 40>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
+        default: return launch_rescale_warp_t<4, 10, 16, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
+    }
 }
 
 int launch_warp_brick(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
