@@ -80,8 +80,9 @@ int dfm_warp_fwd(const void *img, const float *field, void *out,
 /* Fused RescaleTransform(factor >= 1) + linear SpatialTransformer of a one-channel image: the
  * deformation tail of VxmDense at inference (3d_reg.py:305,310; bids_*.py:311-322), where the
  * full-resolution warp is only an intermediate.  out[b,p] = interp(img[b], p + U[b,:,p]) with
- * U = resize(factor * coarse) evaluated on the fly (same arithmetic as dfm_resize_fwd followed
- * by dfm_warp_fwd, bit for bit), so U never touches HBM.
+ * U = resize(factor * coarse) evaluated on the fly, so U never touches HBM (libdfm_exact.so: same
+ * arithmetic as dfm_resize_fwd followed by dfm_warp_fwd, bit for bit; libdfm.so: separable
+ * evaluation of the same interpolation, a few ulp from it).
  *   img [B][Xi][Yi][Zi], coarse [B][3][Xh][Yh][Zh] planar, out [B][X][Y][Z]; cx/cy/cz as in
  *   dfm_resize_fwd (X/Y/Z entries).  work: nullable scratch of B*3*X*Y*Z floats used when the
  *   fused kernel is not applicable (then the two kernels run back to back); without it such

@@ -420,8 +420,9 @@ def rescale_dense_transform(trf, factor, interp_method=LINEAR, out_layout='plana
 
 def rescale_warp(img, coarse_field, factor, fill_value=None):
     """Fused ``RescaleTransform(factor)`` + linear ``SpatialTransformer`` of a one-channel image
-    (dfm.h: dfm_rescale_warp_fwd): identical results to rescale_dense_transform followed by warp,
-    without materialising the full-resolution field.  Inference only (no autograd)."""
+    (dfm.h: dfm_rescale_warp_fwd): the result of rescale_dense_transform followed by warp (bit-identical in
+    the exact build, separable evaluation within a few ulp in the default build) without materialising
+    the full-resolution field.  Inference only (no autograd)."""
     _require_cuda(img, 'img')
     coarse_field = _check_field(coarse_field, 'coarse_field')
     if img.dim() != 5 or img.shape[-1] != 1:
