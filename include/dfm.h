@@ -197,6 +197,33 @@ int dfm_stitch_subvol(const float *tiles, const int *mins, void *out, int T, int
                       int X, int Y, int Z, int out_f64, unsigned flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Losses adjacent to the warp (train_synthmorph.py:301-306) -- the voxel-level parts.
+ *   Dice: vxm.losses.Dice().loss(y_true, y_pred) [UR] on one-hot maps, channels-last [B][N][C]
+ *   (DFM_IMG_CL, the reference layout) or planar [B][C][N]:
+ *     dfm_dice_sums:  sums[b][c] = (sum_n t*p, sum_n t+p) as doubles ([B][C][2], device); the loss is
+ *                     -mean_{b,c} divide_no_nan(2*sums0, sums1), formed by the caller from B*C scalars.
+ *     dfm_dice_bwd:   g_pred[b,n,c] = coef[b][c][0] * y_true[b,n,c] + coef[b][c][1]  (coef fp32, device).
+ *   Grad: vxm.losses.Grad('l2', loss_mult).loss(None, flow) [UR] on a field [B][3][X][Y][Z] planar or
+ *   channels-last (DFM_FIELD_IN_CL):
+ *     dfm_grad_l2_sums: sums[b][axis] = sum of squared forward differences along the axis over all three
+ *                     components ([B][3] doubles); loss[b] = loss_mult/3 * sum_axis sums/count_axis.
+ *     dfm_grad_l2_bwd:  g[b,c,n] = sum_axis coef[b][axis] * ((v[n]-v[n-e]) - (v[n+e]-v[n])), missing
+ *                     neighbours dropped (coef = 2*loss_mult*upstream / (3*count_axis), fp32, device).
+ *   work: caller scratch of dfm_*_workspace_bytes() bytes (per-block partial sums, combined in a fixed
+ *   order: results are deterministic).
+ * ------------------------------------------------------------------------------------- */
+size_t dfm_dice_workspace_bytes(int B, int C, size_t N);
+int dfm_dice_sums(const float *y_true, const float *y_pred, double *sums, void *work, int B, int C, size_t N,
+                  unsigned flags, void *stream);
+int dfm_dice_bwd(const float *y_true, const float *coef, float *g_pred, int B, int C, size_t N, unsigned flags,
+                 void *stream);
+size_t dfm_grad_l2_workspace_bytes(int B, int X, int Y, int Z);
+int dfm_grad_l2_sums(const float *flow, double *sums, void *work, int B, int X, int Y, int Z, unsigned flags,
+                     void *stream);
+int dfm_grad_l2_bwd(const float *flow, const float *coef, float *g, int B, int X, int Y, int Z, unsigned flags,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Layout conversion between the reference's channels-last tensors and planar tensors.
  *   cl [B][N][C]  <->  planar [B][C][N],  elem_size in {1, 2, 4, 8}.
  * ------------------------------------------------------------------------------------- */

@@ -35,6 +35,12 @@ SIGNATURES = {
     'dfm_jacdet_workspace_bytes': (_z, [_i] * 4),
     'dfm_jacdet': (_i, [_p] * 4 + [_i] * 6 + [_u, _p]),
     'dfm_stitch_subvol': (_i, [_p, _p, _p] + [_i] * 8 + [_u, _p]),
+    'dfm_dice_workspace_bytes': (_z, [_i, _i, _z]),
+    'dfm_dice_sums': (_i, [_p, _p, _p, _p, _i, _i, _z, _u, _p]),
+    'dfm_dice_bwd': (_i, [_p, _p, _p, _i, _i, _z, _u, _p]),
+    'dfm_grad_l2_workspace_bytes': (_z, [_i] * 4),
+    'dfm_grad_l2_sums': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),
+    'dfm_grad_l2_bwd': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),
     'dfm_cl_to_planar': (_i, [_p, _p, _i, _i, _z, _i, _p]),
     'dfm_planar_to_cl': (_i, [_p, _p, _i, _i, _z, _i, _p]),
 }

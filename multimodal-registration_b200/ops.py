@@ -542,3 +542,95 @@ def jacobian_determinant(field, out_dtype=torch.float64, want_det=True, want_sta
               int(field.dtype == torch.float64), int(out_dtype == torch.float64),
               _lib.FIELD_IN_CL if f_cl else 0, _stream())
     return det, stats
+
+
+# --------------------------------------------------------------------------------------
+# losses adjacent to the warp (dfm.h: dfm_dice_*, dfm_grad_l2_*)
+# --------------------------------------------------------------------------------------
+def _maps_layout(y_true, y_pred):
+    """Bring two [B, ..., C] maps to ONE common physical layout; returns (true, pred, is_cl)."""
+    lay = layout_of(y_pred)
+    if lay is None:
+        y_pred = y_pred.contiguous()
+        lay = 'cl'
+    if lay == 'both':
+        lay = 'cl'
+    return to_layout(y_true, lay), y_pred, lay == 'cl'
+
+
+class _Dice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_true, y_pred):
+        y_true, y_pred, cl = _maps_layout(y_true.float(), y_pred.float())
+        B, C = int(y_pred.shape[0]), int(y_pred.shape[-1])
+        N = int(y_pred.numel() // max(B * C, 1))
+        lib = _lib.load()
+        sums = torch.empty((B, C, 2), device=y_pred.device, dtype=torch.float64)
+        work = torch.empty(max(lib.dfm_dice_workspace_bytes(B, C, N) // 8, 1), device=y_pred.device, dtype=torch.float64)
+        flags = _lib.IMG_CL if cl else 0
+        _lib.call('dfm_dice_sums', _ptr(y_true), _ptr(y_pred), _ptr(sums), _ptr(work), B, C, N, flags, _stream())
+        top, bottom = 2.0 * sums[..., 0], sums[..., 1]
+        dice = torch.where(bottom != 0, top / torch.where(bottom != 0, bottom, torch.ones_like(bottom)), torch.zeros_like(top))
+        ctx.save_for_backward(y_true, sums)
+        ctx.cl, ctx.shape = cl, tuple(y_pred.shape)
+        return (-dice.mean()).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        y_true, sums = ctx.saved_tensors
+        B, C = ctx.shape[0], ctx.shape[-1]
+        N = int(y_true.numel() // max(B * C, 1))
+        s0, s1 = sums[..., 0], sums[..., 1]
+        ok = s1 != 0
+        s1s = torch.where(ok, s1, torch.ones_like(s1))
+        # loss = -(1/(B C)) sum 2 s0 / s1;  d s0/d p = t,  d s1/d p = 1
+        k = -gout.double() / (B * C)
+        alpha = torch.where(ok, k * 2.0 / s1s, torch.zeros_like(s1))
+        beta = torch.where(ok, -k * 2.0 * s0 / (s1s * s1s), torch.zeros_like(s1))
+        coef = torch.stack([alpha, beta], -1).float().contiguous()
+        g = empty(ctx.shape, 'cl' if ctx.cl else 'planar', y_true.device)
+        _lib.call('dfm_dice_bwd', _ptr(y_true), _ptr(coef), _ptr(g), B, C, N, _lib.IMG_CL if ctx.cl else 0, _stream())
+        return None, g
+
+
+def dice_loss(y_true, y_pred):
+    """``vxm.losses.Dice().loss(y_true, y_pred)`` on [B, X, Y, Z, C] maps: -mean over (batch, channel) of
+    divide_no_nan(2 sum(t p), sum(t + p)) (train_synthmorph.py:305).  Differentiable in y_pred."""
+    _require_cuda(y_pred, 'y_pred')
+    _require_cuda(y_true, 'y_true')
+    if tuple(y_true.shape) != tuple(y_pred.shape):
+        raise ValueError('dice_loss: shapes differ: %s vs %s' % (tuple(y_true.shape), tuple(y_pred.shape)))
+    return _Dice.apply(y_true, y_pred)
+
+
+class _GradL2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, loss_mult):
+        flow, cl = _field_layout(flow.float(), 'flow')
+        B, X, Y, Z, _ = flow.shape
+        lib = _lib.load()
+        sums = torch.empty((B, 3), device=flow.device, dtype=torch.float64)
+        work = torch.empty(max(lib.dfm_grad_l2_workspace_bytes(B, X, Y, Z) // 8, 1), device=flow.device, dtype=torch.float64)
+        _lib.call('dfm_grad_l2_sums', _ptr(flow), _ptr(sums), _ptr(work), B, X, Y, Z, _lib.FIELD_IN_CL if cl else 0, _stream())
+        counts = torch.tensor([(X - 1) * Y * Z * 3, X * (Y - 1) * Z * 3, X * Y * (Z - 1) * 3], device=flow.device, dtype=torch.float64)
+        ctx.save_for_backward(flow, counts)
+        ctx.cl, ctx.mult = cl, float(loss_mult)
+        return ((sums / counts).sum(-1) / 3.0 * float(loss_mult)).float()       # per batch item, like the reference
+
+    @staticmethod
+    def backward(ctx, gout):
+        flow, counts = ctx.saved_tensors
+        B, X, Y, Z, _ = flow.shape
+        coef = (2.0 * ctx.mult / 3.0 * gout.double().reshape(B, 1) / counts.reshape(1, 3)).float().contiguous()
+        g = empty(flow.shape, 'cl' if ctx.cl else 'planar', flow.device)
+        _lib.call('dfm_grad_l2_bwd', _ptr(flow), _ptr(coef), _ptr(g), B, X, Y, Z, _lib.FIELD_IN_CL if ctx.cl else 0, _stream())
+        return g, None
+
+
+def grad_l2_loss(flow, loss_mult=1.0):
+    """``vxm.losses.Grad('l2', loss_mult).loss(None, flow)`` on a [B, X, Y, Z, 3] field: per batch item the
+    mean over the three axes of the mean squared forward difference (train_synthmorph.py:306)."""
+    flow = _check_field(flow, 'flow')
+    if min(flow.shape[1:4]) < 2:
+        raise ValueError('grad_l2_loss: every spatial axis needs at least 2 voxels')
+    return _GradL2.apply(flow, loss_mult)

@@ -1,3 +1,3 @@
 """Mirror of the voxelmorph names on the reference's deformation hot path."""
-from . import layers, networks, utils   # noqa: F401
+from . import layers, losses, networks, utils   # noqa: F401
 from . import py, tf                    # noqa: F401

@@ -143,3 +143,29 @@ def headline_pipeline(svf_half, image, int_steps=7):
     flow = vec_int(svf_half, int_steps)
     flow = rescale_dense_transform(flow, 2)
     return spatial_transformer(image, flow), flow
+
+
+# --------------------------------------------------------------------------------------
+# losses adjacent to the warp (train_synthmorph.py:301-306) -- parity unpinned ([UR] voxelmorph.losses)
+# --------------------------------------------------------------------------------------
+def dice_loss(y_true, y_pred):
+    """vxm.losses.Dice().loss: top = 2 sum(t p), bottom = sum(t + p) over the volume axes,
+    -mean(divide_no_nan(top, bottom)); the same structure as the in-repo losses.py:57-68."""
+    nd = y_pred.dim() - 2
+    axes = tuple(range(1, nd + 1))
+    top = 2 * (y_true * y_pred).sum(axes)
+    bottom = (y_true + y_pred).sum(axes)
+    safe = torch.where(bottom != 0, bottom, torch.ones_like(bottom))
+    dice = torch.where(bottom != 0, top / safe, torch.zeros_like(top))
+    return -dice.mean()
+
+
+def grad_l2_loss(flow, loss_mult=1.0):
+    """vxm.losses.Grad('l2', loss_mult).loss(None, flow): forward differences along every spatial axis,
+    squared, mean over all elements per batch item, averaged over the axes; returns [B]."""
+    nd = flow.dim() - 2
+    terms = []
+    for a in range(1, nd + 1):
+        d = flow.narrow(a, 1, flow.shape[a] - 1) - flow.narrow(a, 0, flow.shape[a] - 1)
+        terms.append((d * d).reshape(flow.shape[0], -1).mean(-1))
+    return sum(terms) / nd * loss_mult

@@ -98,6 +98,29 @@ def main():
         ms = timed(bwd3, n=5)
         report('rescale x2 bwd', ms, B * (12 * NF + 12 * NH), B=B)
 
+    if not which or 'loss' in which:
+        B, C = 2, 26
+        lab = torch.randint(0, C, (B, 160, 160, 192), device='cuda')
+        t = torch.nn.functional.one_hot(lab, C).float()
+        p = torch.rand_like(t).requires_grad_(True)
+        ms = timed(lambda: ops.dice_loss(t, p.detach()), n=5)
+        report('dice sums C=26 (cl)', ms, B * 2 * 4 * C * NF, B=B)
+        loss = ops.dice_loss(t, p)
+        def bwd4():
+            p.grad = None
+            loss.backward(retain_graph=True)
+        ms = timed(bwd4, n=5)
+        report('dice bwd C=26 (cl)', ms, B * 2 * 4 * C * NF, B=B)
+        f = torch.randn(B, 160, 160, 192, 3, device='cuda').requires_grad_(True)
+        ms = timed(lambda: ops.grad_l2_loss(f.detach(), 0.5), n=5)
+        report('grad l2 sums (cl field)', ms, B * 12 * NF, B=B)
+        gl = ops.grad_l2_loss(f, 0.5).sum()
+        def bwd5():
+            f.grad = None
+            gl.backward(retain_graph=True)
+        ms = timed(bwd5, n=5)
+        report('grad l2 bwd (cl field)', ms, B * 24 * NF, B=B)
+
 
 if __name__ == '__main__':
     main()
