@@ -223,6 +223,15 @@ int dfm_grad_l2_sums(const float *flow, double *sums, void *work, int B, int X, 
 int dfm_grad_l2_bwd(const float *flow, const float *coef, float *g, int B, int X, int Y, int Z, unsigned flags,
                     void *stream);
 
+/* d Dice / d field through SpatialTransformer('linear') (train_synthmorph.py:298 + :305) with the Dice
+ * gradient formed on the fly, g[b,n,c] = coef[b][c][0] * y_true[b,n,c] + coef[b][c][1], instead of being
+ * materialised by dfm_dice_bwd and read back by dfm_warp_bwd.  Channels-last maps only (img [B][Ni][C],
+ * y_true [B][N][C]); field planar or channels-last (DFM_FIELD_IN_CL); gfield planar, or channels-last with
+ * DFM_FIELD_OUT_CL; 2 <= C <= 32, or even C <= 64 (else DFM_EUNSUPPORTED: run the two calls). */
+int dfm_warp_dice_bwd(const float *y_true, const float *coef, const float *img, const float *field, float *gfield,
+                      int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill,
+                      unsigned flags, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Layout conversion between the reference's channels-last tensors and planar tensors.
  *   cl [B][N][C]  <->  planar [B][C][N],  elem_size in {1, 2, 4, 8}.

@@ -38,6 +38,7 @@ SIGNATURES = {
     'dfm_dice_workspace_bytes': (_z, [_i, _i, _z]),
     'dfm_dice_sums': (_i, [_p, _p, _p, _p, _i, _i, _z, _u, _p]),
     'dfm_dice_bwd': (_i, [_p, _p, _p, _i, _i, _z, _u, _p]),
+    'dfm_warp_dice_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
     'dfm_grad_l2_workspace_bytes': (_z, [_i] * 4),
     'dfm_grad_l2_sums': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),
     'dfm_grad_l2_bwd': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),

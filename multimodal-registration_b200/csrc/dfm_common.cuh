@@ -55,6 +55,10 @@ int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, 
 int launch_warp_cl_bwd(const float *gout, const float *img, const float *field, float *gimg, float *gfield, int B,
                        int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, unsigned flags,
                        cudaStream_t st);
+// channels-last warp backward with the Dice gradient formed on the fly: upstream g = coef[b][c][0] * y_true + coef[b][c][1]
+int launch_warp_cl_dice_bwd(const float *y_true, const float *coef, const float *img, const float *field, float *gfield,
+                            int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, unsigned flags,
+                            cudaStream_t st);
 // TMA-brick path of the one-channel linear image warp (returns DFM_EUNSUPPORTED if not applicable)
 int launch_warp_brick(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
                       int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st);

@@ -232,6 +232,11 @@ static uint32_t dice_stride(int C, size_t ngroups) {
     if (s > ngroups) s = ((ngroups + C - 1) / C) * (uint64_t)C;
     return (uint32_t)s;
 }
+int launch_dice_finalize(const double *partial, double *sums, int B, int C, int nblk, cudaStream_t st) {
+    dim3 fgrid(2 * C, B);
+    k_dice_finalize<<<fgrid, 128, 0, st>>>(partial, sums, C, nblk);
+    return check_launch("dice finalize");
+}
 static bool vec4_ok(const void *a, const void *b, size_t total) {
     return total % 4 == 0 && (((uintptr_t)a | (uintptr_t)b) & 15u) == 0;
 }
@@ -275,9 +280,7 @@ extern "C" int dfm_dice_sums(const float *y_true, const float *y_pred, double *s
     }
     int rc = check_launch("dfm_dice_sums");
     if (rc) return rc;
-    dim3 fgrid(2 * C, B);
-    k_dice_finalize<<<fgrid, 128, 0, st>>>(partial, sums, C, nblk);
-    return check_launch("dfm_dice_sums(finalize)");
+    return launch_dice_finalize(partial, sums, B, C, nblk, st);
 }
 
 extern "C" int dfm_dice_bwd(const float *y_true, const float *coef, float *g_pred, int B, int C, size_t N, unsigned flags,
@@ -338,4 +341,20 @@ extern "C" int dfm_grad_l2_bwd(const float *flow, const float *coef, float *g, i
     if (flags & DFM_FIELD_IN_CL) k_grad_bwd<true><<<grid, LOSS_THREADS, 0, st>>>(flow, coef, g, X, Y, Z, zd, yd);
     else k_grad_bwd<false><<<grid, LOSS_THREADS, 0, st>>>(flow, coef, g, X, Y, Z, zd, yd);
     return check_launch("dfm_grad_l2_bwd");
+}
+
+// ---------------------------------------------------------------------------------------
+// d Dice / d field through SpatialTransformer('linear') without materialising d Dice / d pred
+// (dfm_warp_cl.cu kernel with the upstream gradient formed on the fly)
+// ---------------------------------------------------------------------------------------
+extern "C" int dfm_warp_dice_bwd(const float *y_true, const float *coef, const float *img, const float *field,
+                                 float *gfield, int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill,
+                                 unsigned flags, void *stream) {
+    DFM_REQUIRE(B >= 0 && C >= 1 && Xi >= 1 && Yi >= 1 && Zi >= 1 && X >= 1 && Y >= 1 && Z >= 1 && B <= 65535, DFM_EINVAL,
+                "dfm_warp_dice_bwd: bad shape");
+    if (B == 0) return DFM_OK;
+    DFM_REQUIRE(y_true && coef && img && field && gfield, DFM_EINVAL, "dfm_warp_dice_bwd: null pointer");
+    int rc = launch_warp_cl_dice_bwd(y_true, coef, img, field, gfield, B, C, Xi, Yi, Zi, X, Y, Z, has_fill, flags, (cudaStream_t)stream);
+    if (rc == DFM_EUNSUPPORTED) return fail(DFM_EUNSUPPORTED, "dfm_warp_dice_bwd: C = %d or shape not supported by the fused kernel", C);
+    return rc;
 }

@@ -46,6 +46,13 @@ template <> __device__ __forceinline__ void ldv<2>(const float *p, float (&a)[2]
     const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
     a[0] = t.x; a[1] = t.y;
 }
+// streaming variants (read once / written once: keep them out of the L1 the corner gathers live in)
+template <int V> __device__ __forceinline__ void ldv_stream(const float *p, float (&a)[V]);
+template <> __device__ __forceinline__ void ldv_stream<1>(const float *p, float (&a)[1]) { a[0] = __ldcs(p); }
+template <> __device__ __forceinline__ void ldv_stream<2>(const float *p, float (&a)[2]) {
+    const float2 t = __ldcs(reinterpret_cast<const float2 *>(p));
+    a[0] = t.x; a[1] = t.y;
+}
 template <int V> __device__ __forceinline__ void stv(float *p, const float (&a)[V]);
 template <> __device__ __forceinline__ void stv<1>(float *p, const float (&a)[1]) { *p = a[0]; }
 template <> __device__ __forceinline__ void stv<2>(float *p, const float (&a)[2]) { *reinterpret_cast<float2 *>(p) = make_float2(a[0], a[1]); }
@@ -130,11 +137,19 @@ struct __align__(16) BwdRec {
     uint32_t pad[3];
 };
 
-template <int CSHIFT, int V, bool MULTI, bool NEED_IMG, bool NEED_FIELD>
-__global__ void __launch_bounds__(256, (NEED_IMG || MULTI) ? 1 : 6)
+// GDICE: `gout` is the map y_true and the upstream gradient is formed on the fly (fusing the Dice SUMS into the
+// forward kernel the same way was measured and lost: a DRAM-latency read inside the gather loop costs 1.11 ms
+// against 0.64 + 0.35 ms for the warp and a separate streaming pass),
+// g[n, c] = coef[b][c][0] * y_true[n, c] + coef[b][c][1] (the Dice gradient, dfm_dice_bwd), never materialised.
+// 4 CTAs/SM (64 registers): the deeper load batching beats the extra warps of a tighter register budget
+// (1.07 ms vs 1.16 ms at 6 CTAs/SM; staging the once-read map in shared memory first: 1.27 ms).
+template <int CSHIFT, int V, bool MULTI, bool NEED_IMG, bool NEED_FIELD, bool GDICE = false>
+__global__ void __launch_bounds__(256, (NEED_IMG || MULTI) ? 1 : 4)
 k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, const float *__restrict__ field,
               float *__restrict__ gimg, float *__restrict__ gfield, int C, int Xi, int Yi, int Zi, uint32_t N,
-              int has_fill, int field_cl, int gfield_cl, FastDiv zdiv, FastDiv ydiv) {
+              int has_fill, int field_cl, int gfield_cl, FastDiv zdiv, FastDiv ydiv,
+              const float *__restrict__ coef = nullptr) {
+    static_assert(!(GDICE && MULTI), "fused Dice gradient needs fixed channels per lane");
     constexpr int CPAD = 1 << CSHIFT, VPW = 32 >> CSHIFT;
     constexpr int CV = VPW > 8 ? VPW : (CSHIFT == 5 ? 4 : 8), RL = CPAD + 1;          // reduction chunk (voxels), row pitch
     __shared__ BwdRec s_rec[8][32];
@@ -187,6 +202,12 @@ k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, con
     const float *pg = gout + (size_t)blockIdx.y * C * N + (size_t)n0 * C + (uint32_t)sub * oC + c0;
     const float *pi = img + (size_t)blockIdx.y * C * Ni + c0;
     float *pq = NEED_IMG ? gimg + (size_t)blockIdx.y * C * Ni + c0 : nullptr;
+    float ca[V], cb[V];                                      // GDICE: coefficients of this lane's channels
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+        ca[u] = (GDICE && lane_on) ? __ldg(coef + ((size_t)blockIdx.y * C + c0 + u) * 2) : 0.f;
+        cb[u] = (GDICE && lane_on) ? __ldg(coef + ((size_t)blockIdx.y * C + c0 + u) * 2 + 1) : 0.f;
+    }
     float mine[3] = {0.f, 0.f, 0.f};                       // gradient of voxel n0 + lane
 #pragma unroll 4
     for (int j0 = 0; j0 < 32; j0 += VPW, pg += VPW * oC) {
@@ -196,7 +217,11 @@ k_warp_cl_bwd(const float *__restrict__ gout, const float *__restrict__ img, con
             const BwdRec r = s_rec[warp][j];
             for (int cc = 0; cc < (MULTI ? C - c0 : 1); cc += 32 * V) {
                 float g[V];
-                ldv<V>(pg + cc, g);
+                ldv_stream<V>(pg + cc, g);
+                if (GDICE) {
+#pragma unroll
+                    for (int u = 0; u < V; ++u) g[u] = fmaf(ca[u], g[u], cb[u]);
+                }
                 if (NEED_FIELD) {
                     const float *p = pi + r.base + cc;
                     float v[8][V];
@@ -328,6 +353,35 @@ int launch_warp_cl_bwd(const float *gout, const float *img, const float *field, 
 #undef DFM_GO2
 #undef DFM_GO
     return check_launch("k_warp_cl_bwd");
+}
+
+// ------------------------------- fused Dice ------------------------------------------------
+static bool dice_shape_ok(int C, bool v2) { return v2 ? (C % 2 == 0 && C <= 64) : C <= 32; }
+
+int launch_warp_cl_dice_bwd(const float *y_true, const float *coef, const float *img, const float *field, float *gfield,
+                            int B, int C, int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, unsigned flags,
+                            cudaStream_t st) {
+    if (!cl_ok(C, Xi, Yi, Zi) || (uint64_t)X * Y * Z * (uint64_t)C >= (1ull << 31)) return DFM_EUNSUPPORTED;
+    const bool v2 = C >= 4 && C % 2 == 0 && aligned8(img) && aligned8(y_true);
+    if (!dice_shape_ok(C, v2)) return DFM_EUNSUPPORTED;
+    const uint32_t N = (uint32_t)X * Y * Z;
+    dim3 grid((N + 255) / 256, B), block(256);
+    const FastDiv zd = make_fastdiv(Z), yd = make_fastdiv(Y);
+    const int fcl = (flags & DFM_FIELD_IN_CL) ? 1 : 0, gcl = (flags & DFM_FIELD_OUT_CL) ? 1 : 0;
+    const int lanes = v2 ? C / 2 : C;
+#define DFM_GO(S, V) k_warp_cl_bwd<S, V, false, false, true, true><<<grid, block, 0, st>>>(y_true, img, field, nullptr, gfield, C, Xi, Yi, Zi, N, has_fill, fcl, gcl, zd, yd, coef)
+#define DFM_GO3(V)                                   \
+    switch (cpad_shift(lanes)) {                     \
+        case 0: case 1: DFM_GO(1, V); break;         \
+        case 2: DFM_GO(2, V); break;                 \
+        case 3: DFM_GO(3, V); break;                 \
+        case 4: DFM_GO(4, V); break;                 \
+        default: DFM_GO(5, V); break;                \
+    }
+    if (v2) { DFM_GO3(2) } else { DFM_GO3(1) }
+#undef DFM_GO3
+#undef DFM_GO
+    return check_launch("k_warp_cl_bwd(dice)");
 }
 
 }  // namespace dfm

@@ -634,3 +634,62 @@ def grad_l2_loss(flow, loss_mult=1.0):
     if min(flow.shape[1:4]) < 2:
         raise ValueError('grad_l2_loss: every spatial axis needs at least 2 voxels')
     return _GradL2.apply(flow, loss_mult)
+
+
+class _WarpDice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, field, y_true, fill_value):
+        B, Xi, Yi, Zi, C = img.shape
+        _, X, Y, Z, _ = field.shape
+        field, f_cl = _field_layout(field, 'field')
+        # forward: the stand-alone warp and a streaming Dice pass (fusing them was measured and is slower);
+        # the warped map is a temporary, only the B*C*2 sums are kept for the backward pass
+        pred = _warp_fwd_raw(img, field, LINEAR, fill_value)
+        lib = _lib.load()
+        sums = torch.empty((B, C, 2), device=img.device, dtype=torch.float64)
+        N = X * Y * Z
+        work = torch.empty(max(lib.dfm_dice_workspace_bytes(B, C, N) // 8, 1), device=img.device, dtype=torch.float64)
+        _lib.call('dfm_dice_sums', _ptr(y_true), _ptr(pred), _ptr(sums), _ptr(work), B, C, N, _lib.IMG_CL, _stream())
+        del pred
+        top, bottom = 2.0 * sums[..., 0], sums[..., 1]
+        dice = torch.where(bottom != 0, top / torch.where(bottom != 0, bottom, torch.ones_like(bottom)), torch.zeros_like(top))
+        ctx.save_for_backward(img, field, y_true, sums)
+        ctx.f_cl, ctx.has_fill = f_cl, fill_value is not None
+        return (-dice.mean()).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, field, y_true, sums = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('warp_dice_loss: gradient with respect to the moving map is not fused; use warp + dice_loss')
+        B, Xi, Yi, Zi, C = img.shape
+        _, X, Y, Z, _ = field.shape
+        s0, s1 = sums[..., 0], sums[..., 1]
+        ok = s1 != 0
+        s1s = torch.where(ok, s1, torch.ones_like(s1))
+        k = -gout.double() / (B * C)
+        coef = torch.stack([torch.where(ok, k * 2.0 / s1s, torch.zeros_like(s1)),
+                            torch.where(ok, -k * 2.0 * s0 / (s1s * s1s), torch.zeros_like(s1))], -1).float().contiguous()
+        gfield = empty(field.shape, 'planar', img.device)
+        _lib.call('dfm_warp_dice_bwd', _ptr(y_true), _ptr(coef), _ptr(img), _ptr(field), _ptr(gfield), B, C, Xi, Yi, Zi,
+                  X, Y, Z, int(ctx.has_fill), _lib.FIELD_IN_CL if ctx.f_cl else 0, _stream())
+        return None, gfield, None, None
+
+
+def warp_dice_loss(img, field, y_true, fill_value=None):
+    """``Dice().loss(y_true, SpatialTransformer('linear')([img, field]))`` on channels-last maps
+    (train_synthmorph.py:298 + :305) without keeping the warped map or materialising the Dice gradient: the
+    backward pass is ONE kernel that forms d Dice / d pred on the fly (dfm.h: dfm_warp_dice_bwd).
+    Differentiable in ``field``.  Channel counts the fused kernel does not cover (odd C > 32, C > 64, planar
+    maps) run the two stand-alone ops."""
+    _require_cuda(img, 'img')
+    _require_cuda(y_true, 'y_true')
+    field = _check_field(field, 'field')
+    C = int(img.shape[-1])
+    fused = (img.dim() == 5 and 2 <= C <= 64 and (C <= 32 or C % 2 == 0) and layout_of(img) in ('cl', 'both') and
+             layout_of(y_true) in ('cl', 'both') and img.dtype == torch.float32 and y_true.dtype == torch.float32 and
+             min(img.shape[1:4]) >= 2 and not img.requires_grad and
+             tuple(y_true.shape) == (img.shape[0],) + tuple(field.shape[1:4]) + (C,))
+    if not fused:
+        return dice_loss(y_true, warp(img, field, LINEAR, fill_value))
+    return _WarpDice.apply(img, field, y_true, fill_value)

@@ -121,6 +121,26 @@ def main():
         ms = timed(bwd5, n=5)
         report('grad l2 bwd (cl field)', ms, B * 24 * NF, B=B)
 
+    if not which or 'fused_dice' in which:
+        B, C = 2, 26
+        svf, _ = bench.synth_inputs(B, 'cpu', 0)
+        flow = ops.rescale_dense_transform(ops.vecint(svf.cuda(), 5), 2)
+        moving = torch.nn.functional.one_hot(torch.randint(0, C, (B, 160, 160, 192), device='cuda'), C).float()
+        fixed = torch.nn.functional.one_hot(torch.randint(0, C, (B, 160, 160, 192), device='cuda'), C).float()
+        nbytes = B * ((8 * C + 12) * NF + (8 * C + 24) * NF)          # warp fwd + d/dfield, the unfused accounting
+        def two_ops():
+            fl = flow.detach().requires_grad_(True)
+            ops.dice_loss(fixed, ops.warp(moving, fl)).backward()
+            return fl.grad
+        def one_op():
+            fl = flow.detach().requires_grad_(True)
+            ops.warp_dice_loss(moving, fl, fixed).backward()
+            return fl.grad
+        ms = timed(two_ops, n=5)
+        report('warp + Dice fwd+bwd C=26, stand-alone ops', ms, nbytes, B=B)
+        ms = timed(one_op, n=5)
+        report('warp + Dice fwd+bwd C=26, fused', ms, nbytes, B=B)
+
 
 if __name__ == '__main__':
     main()

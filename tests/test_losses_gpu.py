@@ -62,3 +62,21 @@ def test_losses_full_size_channels_last_runs_at_stream_speed():
     loss = ops.dice_loss(t, p)
     loss.backward()
     assert -1.0 <= float(loss) <= 0.0 and p.grad.shape == p.shape and ops.layout_of(p.grad) == 'cl'
+
+
+@pytest.mark.parametrize('C', [2, 3, 6, 26, 40])
+@pytest.mark.parametrize('field_layout,fill', [('cl', None), ('planar', 0.0)])
+def test_fused_warp_dice_matches_the_two_ops(C, field_layout, fill):
+    rng = np.random.default_rng(700 + C)
+    shape = (5, 7, 9)
+    img = torch.tensor(rng.random((2,) + shape + (C,)), dtype=torch.float32).cuda()
+    true = torch.tensor(rng.random((2,) + shape + (C,)), dtype=torch.float32).cuda()
+    f = torch.tensor(rng.standard_normal((2,) + shape + (3,)) * 1.5, dtype=torch.float32).cuda()
+    fa = ops.to_layout(f, field_layout).detach().requires_grad_(True)
+    fb = ops.to_layout(f, field_layout).detach().requires_grad_(True)
+    want = ops.dice_loss(true, ops.warp(img, fa, 'linear', fill))
+    want.backward()
+    got = ops.warp_dice_loss(img, fb, true, fill)
+    got.backward()
+    np.testing.assert_allclose(float(got.detach()), float(want.detach()), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(fb.grad.cpu().numpy(), fa.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
