@@ -169,3 +169,18 @@ def grad_l2_loss(flow, loss_mult=1.0):
         d = flow.narrow(a, 1, flow.shape[a] - 1) - flow.narrow(a, 0, flow.shape[a] - 1)
         terms.append((d * d).reshape(flow.shape[0], -1).mean(-1))
     return sum(terms) / nd * loss_mult
+
+
+def dice_loss_zeropad(y_true, y_pred):
+    """losses.py:11-69 as documented (the shipped function raises at :32 before reaching this code): batch
+    item 0 only, voxels where channel 0 of either map is >= 1 are zeroed in every channel, Dice over the
+    channels 1.., -mean(divide_no_nan(top, bottom))."""
+    is0 = (y_true[0, ..., 0] >= 1) | (y_pred[0, ..., 0] >= 1)                  # :38-42
+    keep = (~is0).to(y_pred.dtype)
+    t = torch.stack([y_true[0, ..., i] * keep for i in range(y_pred.shape[-1])])   # :50-56 (channel-major stack)
+    p = torch.stack([y_pred[0, ..., i] * keep for i in range(y_pred.shape[-1])])
+    top = 2 * (t * p).sum((1, 2, 3))                                              # :58-59 (vol_axes on the stacked array)
+    bottom = (t + p).sum((1, 2, 3))
+    top, bottom = top[1:], bottom[1:]                                             # :62-63
+    safe = torch.where(bottom != 0, bottom, torch.ones_like(bottom))
+    return -torch.where(bottom != 0, top / safe, torch.zeros_like(top)).mean()    # :65-68

@@ -80,3 +80,22 @@ def test_fused_warp_dice_matches_the_two_ops(C, field_layout, fill):
     got.backward()
     np.testing.assert_allclose(float(got.detach()), float(want.detach()), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(fb.grad.cpu().numpy(), fa.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
+
+
+def test_dice_loss_zeropad_as_documented():
+    rng = np.random.default_rng(9)
+    C, shape = 6, (6, 7, 8)
+    lab_t = rng.integers(0, C, (2,) + shape)
+    lab_p = rng.integers(0, C, (2,) + shape)
+    t = np.eye(C, dtype=np.float64)[lab_t]
+    p = np.eye(C, dtype=np.float64)[lab_p] * 0.8 + 0.03          # soft prediction; channel 0 >= 1 never ...
+    p[..., 0] = np.where(lab_p == 0, 1.0, p[..., 0])           # ... except where the label is 0 (zero padding)
+    tt = torch.tensor(t)
+    pp = torch.tensor(p, requires_grad=True)
+    want = to.dice_loss_zeropad(tt, pp)
+    want.backward()
+    dp = torch.tensor(p, dtype=torch.float32).cuda().requires_grad_(True)
+    got = vxm.losses.dice_loss_zeropad(torch.tensor(t, dtype=torch.float32).cuda(), dp)
+    got.backward()
+    np.testing.assert_allclose(float(got.detach()), float(want.detach()), rtol=1e-5)
+    np.testing.assert_allclose(dp.grad.cpu().numpy(), pp.grad.numpy(), rtol=1e-4, atol=1e-9)
