@@ -112,25 +112,32 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
 
     // ---- pass 1: own vectors, sample locations, bounding box --------------------------------
     float v[3][TX];
-#pragma unroll
-    for (int i = 0; i < TX; ++i) {
-        const int ic = min(i, nx - 1);
-        const float *pv = ownb + vox0 + ic * XS;
-        v[0][i] = __ldg(pv);
-        v[1][i] = __ldg(pv + N);
-        v[2][i] = __ldg(pv + 2 * (size_t)N);
-    }
     int ox, oy, oz;
     bool fits;
     if (stat) {
-#pragma unroll
-        for (int i = 0; i < TX; ++i)
-            if (SCALED) {
-                v[0][i] = __fmul_rn(scale, v[0][i]); v[1][i] = __fmul_rn(scale, v[1][i]); v[2][i] = __fmul_rn(scale, v[2][i]);
-            }
+        // the tile lies inside its own static brick: the own vectors come from shared memory too
         ox = x0 - HS; oy = yt * TY - HS; oz = zt * TZ - 4;             // brick origin = lower corner index
         fits = true;
+        mbar_wait(&bar, 0);
+        const float *qo = brick + (HS * PX + (yc - oy) * PY + (zc - oz));
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            const int ic = min(i, nx - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[c][i] = qo[c * CS + ic * PX];
+                if (SCALED) v[c][i] = __fmul_rn(scale, v[c][i]);
+            }
+        }
     } else {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            const int ic = min(i, nx - 1);
+            const float *pv = ownb + vox0 + ic * XS;
+            v[0][i] = __ldg(pv);
+            v[1][i] = __ldg(pv + N);
+            v[2][i] = __ldg(pv + 2 * (size_t)N);
+        }
         BoxReduce box;
 #pragma unroll
         for (int i = 0; i < TX; ++i) {
@@ -227,6 +234,105 @@ k_ss_brick(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
             outb[2 * (size_t)N + vox] = __fadd_rn(v2, a[2]);
         }
     }
+}
+
+// -----------------------------------------------------------------------------------------
+// First scaling-and-squaring step of an inference call: the svf arrives channels-last
+// [B][X][Y][Z][3] and is scaled by 2^-nsteps, so its displacements are almost always far below
+// one voxel.  The kernel is OPTIMISTIC: it requests the tile's static-halo brick straight from
+// the channels-last tensor (one TMA box {3*BZ, BY, BX}; a corner is three adjacent floats, lanes
+// stride by 3 floats = conflict-free), reads its own vectors from that brick, and only if some
+// voxel of the CTA turns out to move by a voxel or more does the CTA fall back to per-voxel
+// global gathers.  Output planar; max |out| per batch item goes to `absmax` (static-halo bound of
+// the following steps).  Same arithmetic as k_field_warp_add / k_ss_brick<SCALED>.
+// -----------------------------------------------------------------------------------------
+template <int TX, int BX, int BY, int BZ>
+__global__ void __launch_bounds__(256)
+k_ss_first_cl(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ svf, float *__restrict__ out, int X,
+              int Y, int Z, float scale, FastDiv nzt, float *__restrict__ absmax) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const float *brick = reinterpret_cast<const float *>(smem_raw);   // [BX][BY][BZ][3]
+    __shared__ __align__(8) uint64_t bar;
+    constexpr int PX = BY * BZ, PY = BZ, CS = BX * BY * BZ;
+    constexpr int HS = 1;
+    static_assert(BX >= TX + 2 * HS && BY >= TY + 2 * HS && BZ >= TZ + 4 + 1 + HS, "static halo does not fit the box");
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int yt = (int)fast_div(blockIdx.x, nzt), zt = (int)blockIdx.x - yt * (int)nzt.d;
+    const int z = zt * TZ + lane, y = yt * TY + warp, x0 = blockIdx.y * TX;
+    const bool ok_yz = (z < Z) && (y < Y);
+    const int zc = min(z, Z - 1), yc = min(y, Y - 1);
+    const int nx = min(TX, X - x0);
+    const uint32_t N = (uint32_t)X * Y * Z;
+    const float *srcb = svf + (size_t)blockIdx.z * 3 * N;
+    float *outb = out + (size_t)blockIdx.z * 3 * N;
+    const int mxi = X - 1, myi = Y - 1, mzi = Z - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float fy = (float)yc, fz = (float)zc, fx0 = (float)x0;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + yc) * Z + zc, XS = (uint32_t)Y * Z;
+    const int ox = x0 - HS, oy = yt * TY - HS, oz = zt * TZ - 4;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, 3u * CS * sizeof(float));
+        tma_load_4d(smem_raw, &tmap, &bar, 3 * oz, oy, ox, (int)blockIdx.z);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    float v[3][TX];
+    bool big = false;
+    {
+        const float *qo = brick + 3 * (HS * PX + (yc - oy) * PY + (zc - oz));
+#pragma unroll
+        for (int i = 0; i < TX; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[c][i] = __fmul_rn(scale, qo[3 * min(i, nx - 1) * PX + c]);
+                big |= !(fabsf(v[c][i]) < 0.999f * (float)HS);          // also true for NaN
+            }
+    }
+    const bool fallback = __syncthreads_or(big) != 0;                   // CTA-uniform
+
+    const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
+    const uint32_t GX = (uint32_t)Y * Z, GY = (uint32_t)Z;
+    float am = 0.f;
+    if (ok_yz) {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+            if (i >= nx) break;
+            const float v0 = v[0][i], v1 = v[1][i], v2 = v[2][i];
+            const AxisF ax = axis_fast(__fadd_rn(fx0 + (float)i, v0), mxf, mxi);
+            const AxisF ay = axis_fast(__fadd_rn(fy, v1), myf, myi);
+            const AxisF az = axis_fast(__fadd_rn(fz, v2), mzf, mzi);
+            float w[8], a[3];
+            tri_weights(ax, ay, az, w);
+            if (!fallback) {
+                const float *q = brick + 3 * (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float val[8] = {q[c], q[c + 3], q[c + 3 * PY], q[c + 3 * (PY + 1)],
+                                          q[c + 3 * PX], q[c + 3 * (PX + 1)], q[c + 3 * (PX + PY)], q[c + 3 * (PX + PY + 1)]};
+                    a[c] = tri_accumulate(w, val);
+                }
+            } else {
+                const float *g = srcb + 3 * (size_t)((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float val[8];
+                    gather8(g + c, 3u * GY, 3u * GX, 3u, val);
+                    a[c] = tri_accumulate(w, val);
+                }
+            }
+            const float r0 = __fadd_rn(v0, __fmul_rn(scale, a[0]));
+            const float r1 = __fadd_rn(v1, __fmul_rn(scale, a[1]));
+            const float r2 = __fadd_rn(v2, __fmul_rn(scale, a[2]));
+            am = absmax_fold(absmax_fold(absmax_fold(am, r0), r1), r2);
+            const uint32_t vox = vox0 + i * XS;
+            outb[vox] = r0; outb[N + vox] = r1; outb[2 * (size_t)N + vox] = r2;
+        }
+    }
+    if (absmax) block_absmax_commit(am, absmax + blockIdx.z);          // uniform branch, every thread arrives
 }
 
 // =========================================================================================
@@ -524,6 +630,28 @@ int launch_ss_brick(const float *src, const float *own, float *out, int B, int X
         default: DFM_SS(4, 6, 12, 40, 8, 12, 48);
     }
 #undef DFM_SS
+}
+
+// first SS step from a channels-last svf (optimistic static brick); DFM_EUNSUPPORTED if not applicable
+int launch_ss_first_cl(const float *svf, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
+                       cudaStream_t st) {
+    static const bool off = getenv("DFM_NO_FIRST_CL") != nullptr;      // tuning aid
+    constexpr int TX = 4, BX = 6, BY = 12, BZ = 40;
+    if (off || brick_disabled() || X < 2 || Y < 2 || Z < 4 || !tma_planar_ok(svf, X, Y, 3 * Z) || Z % 4 != 0)
+        return DFM_EUNSUPPORTED;
+    CUtensorMap tmap;
+    if (!encode_map(&tmap, svf, B, X, Y, 3 * Z, BX, BY, 3 * BZ, 1)) return DFM_EUNSUPPORTED;
+    constexpr size_t smem = 3ull * BX * BY * BZ * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_ss_first_cl<TX, BX, BY, BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_ss_first_cl smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int nzt = (Z + TZ - 1) / TZ, nyt = (Y + TY - 1) / TY, nxt = (X + TX - 1) / TX;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    k_ss_first_cl<TX, BX, BY, BZ><<<grid, block, smem, st>>>(tmap, svf, out, X, Y, Z, scale, make_fastdiv(nzt), absmax);
+    return check_launch("k_ss_first_cl");
 }
 
 template <int TX, int BX, int BY, int BZ>

@@ -49,6 +49,9 @@ bool brick_eligible(const float *src, const float *own, const float *out, int Xs
 // bound of |own| for item b; displacements below the brick's static halo skip the box reduction
 int launch_ss_brick(const float *src, const float *own, float *out, int B, int Xs, int Ys, int Zs, int X,
                     int Y, int Z, float scale, int large_box, const float *bound, float bscale, cudaStream_t st);
+// first SS step straight from a channels-last svf: optimistic static brick (dfm_brick.cu)
+int launch_ss_first_cl(const float *svf, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
+                       cudaStream_t st);
 // channels-last multi-channel linear warp, lanes over channels (dfm_warp_cl.cu); DFM_EUNSUPPORTED if not applicable
 int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
                        int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st);

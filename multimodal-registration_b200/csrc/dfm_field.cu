@@ -214,7 +214,7 @@ static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, fl
     if (prefer_direct && !(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
         return launch_fwa1(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st);
     if (brick_eligible(vin, vin, vout, X, Y, Z, X, Y, Z, flags)) {
-        int rc = launch_ss_brick(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, steps_left < 2 ? 1 : 0, bound, bscale, st);
+        int rc = launch_ss_brick(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, steps_left < 3 ? 1 : 0, bound, bscale, st);
         if (rc != DFM_EUNSUPPORTED) return rc;
     }
     if (!(flags & DFM_FIELD_IN_CL) && X >= 2 && Y >= 2 && Z >= 2)
@@ -276,8 +276,12 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
         const bool last = (k == nsteps - 1);
         float *dst = ((nsteps - 1 - k) % 2 == 0) ? out : work;
         unsigned f = cur_cl | (last ? out_cl : 0u);
-        rc = ss_step(cur, dst, B, X, Y, Z, k == 0 ? scale0 : 1.f, f, nsteps - 1 - k,
-                     (measured && k >= 1) ? bound : nullptr, ldexpf(1.f, k - 1), (measured && k == 0) ? bound : nullptr, st);
+        rc = DFM_EUNSUPPORTED;
+        if (k == 0 && in_cl && !(f & DFM_FIELD_OUT_CL))        // channels-last svf: optimistic static brick
+            rc = launch_ss_first_cl(svf, dst, B, X, Y, Z, scale0, measured ? bound : nullptr, st);
+        if (rc == DFM_EUNSUPPORTED)
+            rc = ss_step(cur, dst, B, X, Y, Z, k == 0 ? scale0 : 1.f, f, nsteps - 1 - k,
+                         (measured && k >= 1) ? bound : nullptr, ldexpf(1.f, k - 1), (measured && k == 0) ? bound : nullptr, st);
         if (rc) return rc;
         cur = dst;
         cur_cl = 0u;
