@@ -319,9 +319,9 @@ def run_own(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch PER VOLUME PAIR, from the committed
 # `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
 TRAFFIC_NCU_PER_PAIR = {
-    'ss_step(k_ss_brick)': (59.009e6 + 22.881e6) / 8,
-    'rescale_x2(k_upsample3_march)': (62.914e6 + 415.857e6) / 8,
-    'warp_linear(k_warp_brick)': (629.046e6 + 143.723e6) / 8,
+    'ss_step(k_ss_brick)': (59.009e6 + 22.149e6) / 8,
+    'rescale_x2(k_upsample3_march)': (62.984e6 + 415.512e6) / 8,
+    'warp_linear(k_warp_brick)': (629.240e6 + 144.899e6) / 8,
 }
 
 
