@@ -267,7 +267,7 @@ def run_own(args):
         peak, peak_src = measured_peak_gbs()
         voxels = world * B * N_F
         kernels = {
-            'ss_step(k_ss_brick)': {'launches_per_step': INT_STEPS, 'ms_per_launch': ss_ms / INT_STEPS,
+            'ss_step(k_ss_first_cl, k_ss_brick)': {'launches_per_step': INT_STEPS, 'ms_per_launch': ss_ms / INT_STEPS,
                                     'algorithmic_bytes_per_launch': B * BYTES_SS_STEP, 'in_timed_region': True},
             'rescale_x2(k_upsample3_march)': {'launches_per_step': 1, 'ms_per_launch': rs_ms,
                                            'algorithmic_bytes_per_launch': B * BYTES_RESCALE, 'in_timed_region': True},
@@ -319,7 +319,7 @@ def run_own(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch PER VOLUME PAIR, from the committed
 # `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
 TRAFFIC_NCU_PER_PAIR = {
-    'ss_step(k_ss_brick)': (59.009e6 + 22.149e6) / 8,
+    'ss_step(k_ss_first_cl, k_ss_brick)': (59.009e6 + 22.149e6) / 8,
     'rescale_x2(k_upsample3_march)': (62.984e6 + 415.512e6) / 8,
     'warp_linear(k_warp_brick)': (629.240e6 + 144.899e6) / 8,
 }
