@@ -52,6 +52,13 @@ int launch_ss_brick(const float *src, const float *own, float *out, int B, int X
 // first SS step straight from a channels-last svf: optimistic static brick (dfm_brick.cu)
 int launch_ss_first_cl(const float *svf, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
                        cudaStream_t st);
+// plane-marching SS step through a TMA ring of full-z rows (dfm_ss_march.cu); planar output.
+// variant 0: halo 2, variant 1: halo 4.  first: v = scale*src, max|out| per item -> absmax (nullable).
+// sel (nullable) + sel_mode 1/2: the CTAs of item b run iff (sel[b]*sel_scale < sel_thr) == (sel_mode == 1).
+bool ss_march_eligible(const float *src, int X, int Y, int Z);
+int launch_ss_march(const float *src, float *out, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,
+                    float *absmax, int variant, const float *sel, float sel_scale, float sel_thr, int sel_mode,
+                    cudaStream_t st);
 // channels-last multi-channel linear warp, lanes over channels (dfm_warp_cl.cu); DFM_EUNSUPPORTED if not applicable
 int launch_warp_cl_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
                        int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st);
@@ -119,6 +126,11 @@ __device__ __forceinline__ void upk(u64_t r, float &a, float &b) {
 __device__ __forceinline__ u64_t mul2(u64_t a, u64_t b) {
     u64_t d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64_t add2(u64_t a, u64_t b) {
+    u64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 __device__ __forceinline__ u64_t fma2(u64_t a, u64_t b, u64_t c) {

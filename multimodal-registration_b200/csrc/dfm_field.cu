@@ -222,6 +222,20 @@ static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, fl
     return launch_fwa<DFM_LINEAR>(vin, vin, vout, B, X, Y, Z, X, Y, Z, scale, flags, st, absmax);
 }
 
+// One SS step on the plane-marching kernel (dfm_ss_march.cu).  `bound` (nullable) * bscale bounds the
+// displacements of the step's input: the last two steps pick the halo-2 or the halo-4 ring PER ITEM on the
+// device (both variants are launched; the CTAs of the one not selected exit at once), earlier steps always
+// run halo 2 (|v| halves with every step back; outliers gather from global memory, so this is only tuning).
+static int march_step(const float *vin, float *vout, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,
+                      float *absmax, int steps_left, const float *bound, float bscale, cudaStream_t st) {
+    static const float thr = getenv("DFM_MARCH_THR") ? (float)atof(getenv("DFM_MARCH_THR")) : 3.2f;    // tuning aid
+    if (steps_left >= 2 || !bound)
+        return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 0, nullptr, 0.f, 0.f, 0, st);
+    int rc = launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 0, bound, bscale, thr, 1, st);
+    if (rc) return rc;
+    return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 1, bound, bscale, thr, 2, st);
+}
+
 extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, int X, int Y, int Z,
                               int nsteps, int save_steps, unsigned flags, void *stream) {
     int rc;
@@ -248,6 +262,8 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
     // |v_{k+1}| <= 2 max|v_k| (v_{k+1} = v_k + a convex combination of v_k), so one measured maximum
     // bounds every later step: steps whose bound is below the brick's static halo skip the box reduction
     float *bound = work ? work + (save_steps ? (size_t)nsteps : (size_t)1) * n : nullptr;
+    // the plane-marching kernel serves every step whose source is one of these three buffers
+    const bool march = ss_march_eligible(svf, X, Y, Z) && aligned16(out) && (!work || aligned16(work));
     if (save_steps) {
         // work[k] = v_k (input of step k), k = 0..nsteps-1; v_0 = svf * 2^-nsteps (planar)
         cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)B * sizeof(float), st);
@@ -258,15 +274,21 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
             const float *vin = work + (size_t)k * n;
             float *vout = (k == nsteps - 1) ? out : work + (size_t)(k + 1) * n;
             unsigned f = (k == nsteps - 1) ? out_cl : 0u;
-            rc = ss_step(vin, vout, B, X, Y, Z, 1.f, f, nsteps - 1 - k, bound, ldexpf(1.f, k), nullptr, st);
+            rc = DFM_EUNSUPPORTED;
+            if (march && !f) rc = march_step(vin, vout, B, X, Y, Z, 1.f, false, false, nullptr, nsteps - 1 - k, bound, ldexpf(1.f, k), st);
+            if (rc == DFM_EUNSUPPORTED)
+                rc = ss_step(vin, vout, B, X, Y, Z, 1.f, f, nsteps - 1 - k, bound, ldexpf(1.f, k), nullptr, st);
             if (rc) return rc;
         }
         return DFM_OK;
     }
     // ping-pong between `work` and `out` so that the last step lands in `out`; intermediates planar.
-    // A channels-last svf goes through the gather kernel first, which measures max|v_1| on the way.
-    const bool measured = in_cl && nsteps >= 2;
-    if (measured) {
+    // The first step measures max|v_1| per item on the way (marching kernel, or the channels-last kernels);
+    // `have_bound` is set only once a kernel that writes it has actually been launched, because the brick
+    // kernel's static-halo path trusts the bound without a per-voxel check.
+    const bool want_bound = (in_cl || march) && nsteps >= 2;
+    bool have_bound = false;
+    if (want_bound) {
         cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)B * sizeof(float), st);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "dfm_vecint_fwd: %s", cudaGetErrorString(e));
     }
@@ -276,12 +298,22 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
         const bool last = (k == nsteps - 1);
         float *dst = ((nsteps - 1 - k) % 2 == 0) ? out : work;
         unsigned f = cur_cl | (last ? out_cl : 0u);
+        const float scale = k == 0 ? scale0 : 1.f;
+        float *measure = (want_bound && k == 0) ? bound : nullptr;
+        const float *bnd = (have_bound && k >= 1) ? bound : nullptr;       // bnd * 2^(k-1) bounds the input of step k
         rc = DFM_EUNSUPPORTED;
-        if (k == 0 && in_cl && !(f & DFM_FIELD_OUT_CL))        // channels-last svf: optimistic static brick
-            rc = launch_ss_first_cl(svf, dst, B, X, Y, Z, scale0, measured ? bound : nullptr, st);
-        if (rc == DFM_EUNSUPPORTED)
-            rc = ss_step(cur, dst, B, X, Y, Z, k == 0 ? scale0 : 1.f, f, nsteps - 1 - k,
-                         (measured && k >= 1) ? bound : nullptr, ldexpf(1.f, k - 1), (measured && k == 0) ? bound : nullptr, st);
+        if (march && !(f & DFM_FIELD_OUT_CL)) {
+            rc = march_step(cur, dst, B, X, Y, Z, scale, cur_cl != 0, k == 0, measure, nsteps - 1 - k, bnd, ldexpf(1.f, k - 1), st);
+            if (rc == DFM_OK && measure) have_bound = true;
+        }
+        if (rc == DFM_EUNSUPPORTED && k == 0 && in_cl && !(f & DFM_FIELD_OUT_CL)) {       // channels-last svf: optimistic static brick
+            rc = launch_ss_first_cl(svf, dst, B, X, Y, Z, scale0, measure, st);
+            if (rc == DFM_OK && measure) have_bound = true;
+        }
+        if (rc == DFM_EUNSUPPORTED) {
+            rc = ss_step(cur, dst, B, X, Y, Z, scale, f, nsteps - 1 - k, bnd, ldexpf(1.f, k - 1), (in_cl && k == 0) ? measure : nullptr, st);
+            if (rc == DFM_OK && in_cl && k == 0 && measure) have_bound = true;   // channels-last input runs the gather kernel, which measures
+        }
         if (rc) return rc;
         cur = dst;
         cur_cl = 0u;
