@@ -7,19 +7,41 @@ stream; results come back through pinned buffers too.  This is the path `bench.p
 import numpy as np
 import torch
 
-_PINNED = {}
+import collections
+import os
+
+_PINNED = collections.OrderedDict()      # key -> pinned staging buffer, least recently used first
 _BUSY = {}      # staging buffer key -> event of the last async copy that READ from it
+# Pinned host memory is a scarce resource: the cache is bounded by BYTES and evicts least-recently-used
+# buffers (BIDS runs see a different shape per subject).  Lifetime of `copy=False` views: a view handed out
+# by to_host(copy=False) / predict(copy=False) stays valid while its buffer is cached; an evicted buffer is
+# only dropped from the cache -- the numpy view keeps the pinned allocation alive -- but a later call with
+# the same (shape, dtype, tag) REUSES the buffer and overwrites the view.
+PINNED_CACHE_BYTES = int(os.environ.get('DFM_PINNED_CACHE_MB', '4096')) << 20
+
+
+def _nbytes(buf):
+    return buf.numel() * buf.element_size()
 
 
 def _pinned(shape, dtype, tag):
     key = (tuple(shape), dtype, tag)
     buf = _PINNED.get(key)
     if buf is None:
-        if len(_PINNED) > 64:
-            _PINNED.clear()
-            _BUSY.clear()
         buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         _PINNED[key] = buf
+        total = sum(_nbytes(b) for b in _PINNED.values())
+        while total > PINNED_CACHE_BYTES and len(_PINNED) > 1:
+            old_key, old = next(iter(_PINNED.items()))
+            if old_key == key:
+                break
+            ev = _BUSY.pop(old_key, None)
+            if ev is not None:
+                ev.synchronize()
+            del _PINNED[old_key]
+            total -= _nbytes(old)
+    else:
+        _PINNED.move_to_end(key)
     ev = _BUSY.get(key)
     if ev is not None:
         ev.synchronize()          # an earlier H2D copy may still be reading this buffer

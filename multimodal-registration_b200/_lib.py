@@ -47,8 +47,15 @@ SIGNATURES = {
 }
 
 
+DFM_OK, DFM_EINVAL, DFM_EALIGN, DFM_EUNSUPPORTED, DFM_ECUDA = 0, -1, -2, -3, -4
+
+
 class DfmError(RuntimeError):
-    pass
+    """Raised for every failed library call; ``code`` is the DFM_E* return value (None for loader errors)."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 _libs = {}
@@ -94,7 +101,7 @@ def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
-        raise DfmError('%s failed (%d): %s' % (name, rc, lib.dfm_last_error().decode()))
+        raise DfmError('%s failed (%d): %s' % (name, rc, lib.dfm_last_error().decode()), rc)
 
 
 def version():

@@ -564,6 +564,142 @@ k_warp_brick(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// One-channel linear image warp with a VARIABLE brick: 8 x 8 x 16 voxels per CTA (warp = two y rows x 16 z,
+// each thread walks 4 x planes).
+// On strongly deforming fields (bench: std-3 SVF, |grad u| ~ 0.23 at full resolution, |u| up to 17 voxels)
+// the bounding box of a tile is dominated by its slant along the long z edge: a 4 x 8 x 32 tile needs
+// 11 x 14 x 34 voxels in the median and fits the fixed 10 x 16 x 48 box of k_warp_brick in 28 % of the cases;
+// any fixed box that fits >= 94 % of the tiles is >= 11 x the tile (L2 -> SM traffic).  Here the box is cut to
+// the tile: the brick is loaded as ONE TMA BOX PER X PLANE, as many planes as the bounding box has, each
+// {BZ, BY} with BY in {12, 16, 20, 24} and BZ in {24, 32} picked per CTA from eight tensor maps -- 97 % of the
+// bench tiles fit 36 KB at 4.6 x the tile on average (the single 18 x 18 x 24 box: 76 % at 5.8 x).
+// Two rows per warp cost a 2-way bank conflict on most gathers; the one-channel warp has 8 gathers per voxel
+// and is nowhere near the shared-memory limit (the SS step, with 24, is).
+// Same arithmetic as k_warp_brick (FMODE 0 / 1); tiles that do not fit gather from global memory.
+// -----------------------------------------------------------------------------------------
+struct WarpMaps {
+    CUtensorMap m[4][2];            // [BY = 12 + 4 i][BZ = 24 + 8 j], box {BZ, BY, 1, 1}
+};
+
+template <bool FIELD_CL, bool HF>
+__global__ void __launch_bounds__(256)
+k_warp_brick_var(const __grid_constant__ WarpMaps maps, const float *__restrict__ img, const float *__restrict__ field,
+                 float *__restrict__ out, int Xi, int Yi, int Zi, int X, int Y, int Z, float fill, FastDiv nzt, int cap_floats) {
+    constexpr int TXC = 8, TYC = 8, TZC = 16, NX = 4;          // CTA tile; x planes per thread
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *brick = reinterpret_cast<float *>(smem_raw);        // [ex][BY][BZ]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_min[3], s_max[3];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int yt = (int)fast_div(blockIdx.x, nzt), zt = (int)blockIdx.x - yt * (int)nzt.d;
+    const int z = zt * TZC + (lane & 15), y = yt * TYC + 2 * (warp & 3) + (lane >> 4), x0 = blockIdx.y * TXC + (warp >> 2) * NX;
+    const bool ok_yz = (z < Z) && (y < Y);
+    const int zc = min(z, Z - 1), yc = min(y, Y - 1);
+    const uint32_t N = (uint32_t)X * Y * Z, Ni = (uint32_t)Xi * Yi * Zi;
+    const float *fb = field + (size_t)blockIdx.z * 3 * N;
+    float *outb = out + (size_t)blockIdx.z * N;
+    const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float fy = (float)yc, fz = (float)zc;
+    const int nx = min(NX, X - x0);                            // per half-CTA; may be <= 0 past the volume edge
+    const int x0c = min(x0, X - 1);
+    const uint32_t XS = (uint32_t)Y * Z, vox0 = ((uint32_t)x0c * Y + yc) * Z + zc;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        s_min[0] = s_min[1] = s_min[2] = INT_MAX;
+        s_max[0] = s_max[1] = s_max[2] = INT_MIN;
+    }
+    __syncthreads();
+
+    float l[3][NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const uint32_t vox = vox0 + (uint32_t)min(i, max(nx, 1) - 1) * XS;     // shadow the last valid plane
+        if (FIELD_CL) {
+            l[0][i] = __ldg(fb + (size_t)vox * 3); l[1][i] = __ldg(fb + (size_t)vox * 3 + 1); l[2][i] = __ldg(fb + (size_t)vox * 3 + 2);
+        } else {
+            l[0][i] = __ldg(fb + vox); l[1][i] = __ldg(fb + N + vox); l[2][i] = __ldg(fb + 2 * (size_t)N + vox);
+        }
+    }
+    BoxReduce box;
+    uint32_t oob = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const float lx = __fadd_rn((float)(x0c + min(i, max(nx, 1) - 1)), l[0][i]);
+        const float ly = __fadd_rn(fy, l[1][i]);
+        const float lz = __fadd_rn(fz, l[2][i]);
+        if (HF && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) oob |= 1u << i;
+        l[0][i] = axis_clip(lx, mxf); l[1][i] = axis_clip(ly, myf); l[2][i] = axis_clip(lz, mzf);
+        if (i == 0) box.first(l[0][i], l[1][i], l[2][i]); else box.add(l[0][i], l[1][i], l[2][i]);
+    }
+    box.commit(s_min, s_max, mxi, myi, mzi);
+    __syncthreads();
+    const int ox = s_min[0] - 1, oy = s_min[1] - 1, oz = (s_min[2] - 1) & ~3;                  // lower corner index
+    const int ex = s_max[0] - ox + 1, ey = s_max[1] - oy + 1, ez = s_max[2] - oz + 1;          // extents of the corner indices
+    const int iy = max((ey + 3) / 4 - 3, 0), iz = ez <= 24 ? 0 : 1;                            // BY = 12 + 4 iy, BZ = 24 + 8 iz
+    const int PY = 24 + 8 * iz, PX = (12 + 4 * iy) * PY;
+    const bool fits = (iy <= 3) && (ez <= 32) && (ex * PX <= cap_floats);                       // CTA-uniform
+    if (fits) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)(ex * PX * sizeof(float)));
+            // one box per x plane from the map whose {BZ, BY} covers the bounding box (constant indices: the
+            // tensor maps must be addressed in parameter space)
+#define DFM_PLANES(I, J)                                                                                   \
+    case (I) * 2 + (J):                                                                                    \
+        for (int p = 0; p < ex; ++p) tma_load_4d(brick + p * PX, &maps.m[I][J], &bar, oz, oy, ox + p, (int)blockIdx.z); \
+        break;
+            switch (iy * 2 + iz) {
+                DFM_PLANES(0, 0) DFM_PLANES(0, 1) DFM_PLANES(1, 0) DFM_PLANES(1, 1)
+                DFM_PLANES(2, 0) DFM_PLANES(2, 1) DFM_PLANES(3, 0) DFM_PLANES(3, 1)
+            }
+#undef DFM_PLANES
+        }
+        mbar_wait(&bar, 0);
+    }
+    if (!ok_yz || nx <= 0) return;
+    const int cbase = -((ox + 1) * PX + (oy + 1) * PY + (oz + 1));
+    if (fits) {
+#pragma unroll
+        for (int i = 0; i < NX; i += 2) {
+            if (i >= nx) break;
+            const bool hasB = i + 1 < nx;
+            const AxisF ax = axis_from_clipped(l[0][i], mxi), ay = axis_from_clipped(l[1][i], myi), az = axis_from_clipped(l[2][i], mzi);
+            const AxisF bx = axis_from_clipped(l[0][i + 1], mxi), by = axis_from_clipped(l[1][i + 1], myi), bz = axis_from_clipped(l[2][i + 1], mzi);
+            float wA[8], wB[8];
+            tri_weights_pair(ax, ay, az, bx, by, bz, wA, wB);
+            const float *qa = brick + (ax.i1 * PX + ay.i1 * PY + az.i1 + cbase), *qa1 = qa + PY, *qa2 = qa + PX, *qa3 = qa2 + PY;
+            const float *qb = brick + (bx.i1 * PX + by.i1 * PY + bz.i1 + cbase), *qb1 = qb + PY, *qb2 = qb + PX, *qb3 = qb2 + PY;
+            const float va[8] = {qa[0], qa[1], qa1[0], qa1[1], qa2[0], qa2[1], qa3[0], qa3[1]};
+            const float vb[8] = {qb[0], qb[1], qb1[0], qb1[1], qb2[0], qb2[1], qb3[0], qb3[1]};
+            float ra, rb;
+            tri_accumulate_pair(wA, wB, va, vb, ra, rb);
+            if (HF) {
+                if (oob & (1u << i)) ra = fill;
+                if (oob & (2u << i)) rb = fill;
+            }
+            outb[vox0 + i * XS] = ra;
+            if (hasB) outb[vox0 + (i + 1) * XS] = rb;
+        }
+    } else {
+        const float *ib = img + (size_t)blockIdx.z * Ni;
+        const uint32_t GX = (uint32_t)Yi * Zi, GY = (uint32_t)Zi;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            if (i >= nx) break;
+            const AxisF ax = axis_from_clipped(l[0][i], mxi), ay = axis_from_clipped(l[1][i], myi), az = axis_from_clipped(l[2][i], mzi);
+            float w[8], val[8];
+            tri_weights(ax, ay, az, w);
+            gather8(ib + ((uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1)), GY, GX, 1u, val);
+            float r = tri_accumulate(w, val);
+            if (HF && (oob & (1u << i))) r = fill;
+            outb[vox0 + i * XS] = r;
+        }
+    }
+}
+
 // ------------------------------- host side -----------------------------------------------
 static bool brick_disabled() {
     static const bool d = getenv("DFM_NO_BRICK") != nullptr;   // debugging aid: force direct gathers
@@ -760,6 +896,45 @@ int launch_rescale_warp(const float *img, const float *half, float *out, const f
     }
 }
 
+static int launch_warp_brick_var(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
+                                 int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
+    WarpMaps maps;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (!encode_map(&maps.m[i][j], img, B, Xi, Yi, Zi, 1, 12 + 4 * i, 24 + 8 * j, 1)) return DFM_EUNSUPPORTED;
+    // Brick bytes per CTA.  The kernel is latency-bound (field load -> box reduction -> TMA -> gather is one serial
+    // chain per tile; ncu: long-scoreboard stalls 7.5 per issue), so resident CTAs count for more than the last
+    // few percent of fit rate: measured on the bench field at B=32 (carve-out 80 %): 20 KB 0.92 ms, 24 KB 0.85 ms,
+    // 28 KB 0.81 ms, 32 KB 0.86 ms, 36 KB 0.85 ms, 40 KB 0.99 ms (k_warp_brick, fixed 30 KB box: 0.93 ms).
+    static const int cap_kb = getenv("DFM_WARP_CAP_KB") ? atoi(getenv("DFM_WARP_CAP_KB")) : 28;      // tuning aid
+    const size_t smem = (size_t)cap_kb * 1024;
+    static bool configured = false;
+    const int carve = getenv("DFM_WARP_CARVEOUT") ? atoi(getenv("DFM_WARP_CARVEOUT")) : 80;       // leaves L1 for the field / output streams
+#define DFM_CFGV(FC, HFv)                                                                                                   \
+    {                                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(k_warp_brick_var<FC, HFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_warp_brick_var smem attribute: %s", cudaGetErrorString(e));             \
+        cudaFuncSetAttribute(k_warp_brick_var<FC, HFv>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);             \
+    }
+    if (!configured) {
+        DFM_CFGV(false, false) DFM_CFGV(false, true) DFM_CFGV(true, false) DFM_CFGV(true, true)
+        configured = true;
+    }
+#undef DFM_CFGV
+    const int nzt = (Z + 15) / 16, nyt = (Y + 7) / 8, nxt = (X + 7) / 8;
+    dim3 grid(nzt * nyt, nxt, B), block(256);
+    const FastDiv nz = make_fastdiv(nzt);
+    const int cap = (int)(smem / sizeof(float));
+#define DFM_WBV(FC, HFv) k_warp_brick_var<FC, HFv><<<grid, block, smem, st>>>(maps, img, field, out, Xi, Yi, Zi, X, Y, Z, fill, nz, cap)
+    if (flags & DFM_FIELD_IN_CL) {
+        if (has_fill) DFM_WBV(true, true); else DFM_WBV(true, false);
+    } else {
+        if (has_fill) DFM_WBV(false, true); else DFM_WBV(false, false);
+    }
+#undef DFM_WBV
+    return check_launch("k_warp_brick_var");
+}
+
 int launch_warp_brick(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
                       int Y, int Z, int has_fill, float fill, unsigned flags, cudaStream_t st) {
     static const bool direct = getenv("DFM_WARP_DIRECT") != nullptr;   // tuning aid
@@ -767,13 +942,14 @@ int launch_warp_brick(const float *img, const float *field, float *out, int B, i
     if (!tma_source_ok(img, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
     static const int cfg = getenv("DFM_WARP_CFG") ? atoi(getenv("DFM_WARP_CFG")) : 0;
     switch (cfg) {
+        case 0: return launch_warp_brick_var(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 1: return launch_warp_brick_t<4, 10, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 2: return launch_warp_brick_t<8, 16, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 3: return launch_warp_brick_t<4, 10, 18, 72>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 4: return launch_warp_brick_t<8, 14, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 5: return launch_warp_brick_t<4, 8, 12, 40>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
         case 6: return launch_warp_brick_t<4, 8, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);    // round-1 kernel (cfg 20)
     }
 }
 

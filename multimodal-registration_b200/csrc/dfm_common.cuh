@@ -53,7 +53,7 @@ int launch_ss_brick(const float *src, const float *own, float *out, int B, int X
 int launch_ss_first_cl(const float *svf, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
                        cudaStream_t st);
 // plane-marching SS step through a TMA ring of full-z rows (dfm_ss_march.cu); planar output.
-// variant 0: halo 2, variant 1: halo 4.  first: v = scale*src, max|out| per item -> absmax (nullable).
+// variant 0: halo 2, variant 1: halo 3.  first: v = scale*src, max|out| per item -> absmax (nullable).
 // sel (nullable) + sel_mode 1/2: the CTAs of item b run iff (sel[b]*sel_scale < sel_thr) == (sel_mode == 1).
 bool ss_march_eligible(const float *src, int X, int Y, int Z);
 int launch_ss_march(const float *src, float *out, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,

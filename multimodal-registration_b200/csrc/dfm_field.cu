@@ -223,8 +223,8 @@ static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, fl
 }
 
 // One SS step on the plane-marching kernel (dfm_ss_march.cu).  `bound` (nullable) * bscale bounds the
-// displacements of the step's input: the last two steps pick the halo-2 or the halo-4 ring PER ITEM on the
-// device (both variants are launched; the CTAs of the one not selected exit at once), earlier steps always
+// displacements of the step's input: the last two steps pick the halo-2 or the halo-3 ring PER ITEM on the
+// device (both variants are launched; the CTAs of the one not selected skip the item), earlier steps always
 // run halo 2 (|v| halves with every step back; outliers gather from global memory, so this is only tuning).
 static int march_step(const float *vin, float *vout, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,
                       float *absmax, int steps_left, const float *bound, float bscale, cudaStream_t st) {

@@ -54,7 +54,7 @@ k_jacdet(const Tin *__restrict__ field, Tout *__restrict__ det, double *__restri
     if (!partials) return;
     // block reduction in a fixed order -> deterministic statistics
     double s = valid ? dval : 0.0, s2 = valid ? dval * dval : 0.0;
-    double nn = (valid && dval < 0.0) ? 1.0 : 0.0;
+    double nn = (valid && !(dval > 0.0) && dval != 0.0) ? 1.0 : 0.0;   // np.count_nonzero(np.where(det > 0, 0, det)): negatives and NaN
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_down_sync(0xffffffffu, s, o);
@@ -209,8 +209,8 @@ k_jacdet_tiled(const __grid_constant__ CUtensorMap tmap, Tout *__restrict__ det,
                     if (pair_store) store_pair(q, da, db);                                                            \
                     else { q[0] = (Tout)da; if (ok1) q[1] = (Tout)db; }                                               \
                 }                                                                                                     \
-                s += da; s2 += da * da; nn += (da < 0.0) ? 1.0 : 0.0;                                                 \
-                if (ok1) { s += db; s2 += db * db; nn += (db < 0.0) ? 1.0 : 0.0; }                                    \
+                s += da; s2 += da * da; nn += (!(da > 0.0) && da != 0.0) ? 1.0 : 0.0;                                                 \
+                if (ok1) { s += db; s2 += db * db; nn += (!(db > 0.0) && db != 0.0) ? 1.0 : 0.0; }                                    \
             }                                                                                                         \
         }                                                                                                             \
         __syncthreads();   /* every reader of plane p - 2's predecessor slots is done */                              \

@@ -8,19 +8,28 @@
 // bank = z mod 32 whatever the row.  With full-z rows the z halo disappears, and the x/y halo only
 // has to cover the displacement, not the tile's slant.
 //
-// Structure (one CTA = TY y-rows x all z, marching along x over one x segment):
-//  * warp-specialised: TY*NZW consumer warps (warp = one y row x 32 z, lane = z) + 1 producer warp.
+// Structure (one persistent CTA = TY y-rows x all z, marching along x):
+//  * warp-specialised: TY/VPT*NZW consumer warps (warp = VPT y rows x 32 z, lane = z) + 1 producer warp.
 //  * the producer streams x planes {rows y0-H .. y0+TY-1+H, all z, 3 components} through an R-slot
 //    ring, one TMA box per plane (NZW boxes of 32 z x 3 for a channels-last source), `full` mbarrier
 //    per slot (expect_tx), `empty` mbarrier per slot (one arrival per consumer warp).
-//  * a consumer thread owns one (y, z) column and marches x: own vector from the ring's centre plane
-//    (no global loads at all besides the TMA), 24 corner LDS with immediate offsets, stores planar.
+//  * a consumer thread owns VPT (y, z) columns and marches x: own vectors from the ring's centre plane
+//    (no global loads at all besides the TMA), 24 corner LDS with immediate offsets, stores planar.  In the
+//    default build the two voxels of a thread share packed f32x2 maths (FADD2 / FMUL2 / FFMA2).
 //  * static halo H: a voxel whose corners lie within +-H planes / rows is served by the ring.  The test
 //    is on the integer corner indices, per warp (`__all_sync`); a warp with an outlier lane gathers
 //    from global memory instead, so results never depend on H (bit-identical to the other kernels).
 //    On the bench field (std-3 SVF) H = 2 serves 99.7 % of the warps up to the second-last step
-//    and H = 4 99.8 % of the last step -- the field's maximum is far above its typical magnitude.
-//  * L2 -> SM amplification (TY + 2H)/TY * (seg + 2H)/seg instead of the brick's 2.8-3.75.
+//    and H = 3 96.9 % of the last step -- the field's maximum is far above its typical magnitude.
+//  * L2 -> SM amplification (TY + 2H)/TY (+ 2H planes per ~86-step range) instead of the brick's 2.8-3.75.
+//
+// Measured (B200, B=32 x 80x80x96, ncu in profiles/r2_*): 116-118 us per halo-2 step (was 144 us with the
+// bounding-box brick), 62 % of the HBM roofline.  The kernel is bound by the SHARED-MEMORY DATA PIPE:
+// 27 loads + 3 stores per voxel are 35 wavefronts per 32 voxels (84 % of the pipe's peak in the profile);
+// the remaining bank conflicts are the pigeonhole kind -- a warp whose 32 lanes span 33 columns because the
+// field stretches along z.  Experiments that isolate one pipe (scripts/exp/exp_march.cu): without the upper x
+// plane's 12 loads 103 us, without any corner load 87 us (the streaming floor of the ring), with trivial
+// weights 115 us -- time follows the shared-memory loads, not the instruction count.
 //
 // Reference semantics: vxm.utils.integrate_vec, one squaring step.
 #include <cuda.h>
@@ -28,6 +37,10 @@
 
 #include "dfm_common.cuh"
 #include "dfm_tma.cuh"
+
+#ifndef MARCH_EXP
+#define MARCH_EXP 0          // scripts/exp/exp_march.cu: deliberately wrong variants that isolate one pipe
+#endif
 
 namespace dfm {
 
@@ -69,12 +82,22 @@ constexpr int march_ctas(int TY, int H, int R, int NZW) {
     return (R * 3 * (TY + 2 * H) * NZW * 32 * 4 + 2048) * 2 <= 227 * 1024 ? 2 : 1;
 }
 
+// Work decomposition: the B * nstrips * X plane-steps of a launch form one sequence (item = (batch item,
+// y strip), then x); CTA c of a PERSISTENT grid owns the contiguous range [c T/G, (c+1) T/G).  Inside a range
+// the ring streams without interruption -- also across the boundary between two strips, where the producer
+// has the next strip's first planes in flight while the consumers finish the previous one -- so the pipeline
+// fills once per CTA instead of once per tile, every CTA does the same number of steps (no wave tail), and
+// the x halo is re-read once per range (~86 steps) instead of once per segment.
+struct MarchRun {
+    int b, y0, xs, xe, p_first, p_last;
+};
+
 // TY rows per CTA, VPT of them per thread (rows ty, ty + TY/VPT, ...): the per-step overhead (ring
 // bookkeeping, barrier wait / arrive, loop) is shared by VPT voxels and their gathers interleave.
 template <int TY, int VPT, int H, int R, int NZW, bool IN_CL, bool FIRST>
 __global__ void __launch_bounds__((TY / VPT * NZW + 1) * 32, march_ctas(TY, H, R, NZW))
 k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ out, int X,
-           int Y, int Z, float scale, int seglen, float *__restrict__ absmax, MarchSel sel) {
+           int Y, int Z, float scale, int nstrips, unsigned long long total, float *__restrict__ absmax, MarchSel sel) {
     constexpr int ZP = NZW * 32, ROWS = TY + 2 * H, TYW = TY / VPT, NCW = TYW * NZW;
     constexpr int CS = ROWS * ZP;          // planar: component stride in a slot; channels-last: sub-box (32 z x 3) stride / 3
     constexpr int SLOT = 3 * CS;           // floats per ring slot (one x plane)
@@ -84,17 +107,8 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     float *ring = reinterpret_cast<float *>(smem_raw);
     __shared__ __align__(8) uint64_t full[R], empty[R];
 
-    const int b = blockIdx.z;
-    if (sel.mode) {                                                    // CTA-uniform variant selection
-        const bool below = __ldg(sel.sel + b) * sel.scale < sel.thr;    // false for NaN
-        if ((sel.mode == 1) != below) return;
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xs = blockIdx.x * seglen, xe = min(xs + seglen, X);
-    const int y0 = blockIdx.y * TY;
-    const int p_first = max(xs - H, 0), p_last = min(xe - 1 + H, X - 1);
     const uint32_t N = (uint32_t)X * Y * Z;
-
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < R; ++i) {
@@ -105,67 +119,94 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     __syncthreads();
     const uint32_t full_u = smem_u32(&full[0]), empty_u = smem_u32(&empty[0]);
 
-    int am = 0;                                                        // max |out| as float bits (NaN orders above +inf)
+    uint32_t t = (uint32_t)(total * blockIdx.x / gridDim.x);          // total < 2^32 (host)
+    const uint32_t t1 = (uint32_t)(total * (blockIdx.x + 1) / gridDim.x);
+    // next run of this CTA's range (identical in every thread): false when the range is exhausted
+    auto next_run = [&](MarchRun &r) -> bool {
+        while (t < t1) {
+            const uint32_t item = t / (uint32_t)X;
+            r.xs = (int)(t - item * (uint32_t)X);
+            r.b = (int)(item / (uint32_t)nstrips);
+            r.y0 = (int)(item - (uint32_t)r.b * (uint32_t)nstrips) * TY;
+            r.xe = (int)min((uint32_t)X, (uint32_t)r.xs + (t1 - t));
+            t += (unsigned)(r.xe - r.xs);
+            if (sel.mode) {                                            // per-item variant selection
+                const bool below = __ldg(sel.sel + r.b) * sel.scale < sel.thr;     // false for NaN
+                if ((sel.mode == 1) != below) continue;
+            }
+            r.p_first = max(r.xs - H, 0);
+            r.p_last = min(r.xe - 1 + H, X - 1);
+            return true;
+        }
+        return false;
+    };
+
     if (warp == NCW) {
         // ------------------------------ producer ------------------------------------------
         if (lane == 0) {
-            const int nplanes = p_last - p_first + 1;
             int s = 0;
-            uint32_t ph = 1;                                           // parity of the previous use of the slot
-            for (int q = 0; q < nplanes; ++q) {
-                if (q >= R) mbar_wait_u(empty_u + 8 * s, ph);
-                mbar_expect_tx(&full[s], (uint32_t)(SLOT * sizeof(float)));
-                float *dst = ring + s * SLOT;
-                if (IN_CL) {
+            uint32_t ph = 1, q = 0;                                    // ph: parity of the previous use of the slot
+            MarchRun r;
+            while (next_run(r)) {
+                for (int p = r.p_first; p <= r.p_last; ++p, ++q) {
+                    if (q >= R) mbar_wait_u(empty_u + 8 * s, ph);
+                    mbar_expect_tx(&full[s], (uint32_t)(SLOT * sizeof(float)));
+                    float *dst = ring + s * SLOT;
+                    if (IN_CL) {
 #pragma unroll
-                    for (int j = 0; j < NZW; ++j) tma_load_4d(dst + j * (ROWS * 96), &tmap, &full[s], 96 * j, y0 - H, p_first + q, b);
-                } else {
-                    tma_load_4d(dst, &tmap, &full[s], 0, y0 - H, p_first + q, b * 3);
+                        for (int j = 0; j < NZW; ++j) tma_load_4d(dst + j * (ROWS * 96), &tmap, &full[s], 96 * j, r.y0 - H, p, r.b);
+                    } else {
+                        tma_load_4d(dst, &tmap, &full[s], 0, r.y0 - H, p, r.b * 3);
+                    }
+                    if (++s == R) { s = 0; ph ^= 1u; }
                 }
-                if (++s == R) { s = 0; ph ^= 1u; }
             }
         }
-    } else {
-        // ------------------------------ consumers -----------------------------------------
-        const int tyw = warp / NZW, zw = warp - tyw * NZW;
-        const int z = zw * 32 + lane;
-        const int zc = min(z, Z - 1);                                  // threads past the edge shadow the last voxel
-        const int mxi = X - 1, myi = Y - 1, mzi = Z - 1;
-        const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
-        const float fz = (float)zc;
-        const int rb1 = y0 - H + 1;                                    // ring row r holds volume row y0 - H + r
-        const float *srcb = src + (size_t)b * 3 * N;
-        const uint32_t XS = (uint32_t)Y * Z, GX = XS, GY = (uint32_t)Z;
+        return;
+    }
+    // ------------------------------ consumers -----------------------------------------
+    const int tyw = warp / NZW, zw = warp - tyw * NZW;
+    const int z = zw * 32 + lane;
+    const int zc = min(z, Z - 1);                                      // threads past the edge shadow the last voxel
+    const int mxi = X - 1, myi = Y - 1, mzi = Z - 1;
+    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float fz = (float)zc;
+    const uint32_t XS = (uint32_t)Y * Z, GX = XS, GY = (uint32_t)Z;
+    const float *const ring_end = ring + R * SLOT;
+    uint32_t wa = full_u, wph = 0;                                     // next plane (in load order) to wait for
+    int wq = 0, rq = 0, rslot = 0;                                     // planes waited for / loaded before this run; slot of the run's first plane
+    MarchRun r;
+    while (next_run(r)) {
+        const int rb1 = r.y0 - H + 1;                                  // ring row k holds volume row y0 - H + k
         float fy[VPT];
         int own_off[VPT];
         float *op[VPT];                                                // output pointer of component 0 at plane x
         bool ok[VPT];
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
-            const int y = y0 + tyw + j * TYW, yc = min(y, Y - 1);
+            const int y = r.y0 + tyw + j * TYW, yc = min(y, Y - 1);
             ok[j] = (z < Z) && (y < Y);
             fy[j] = (float)yc;
-            own_off[j] = IN_CL ? ((zc >> 5) * (ROWS * 96) + (yc - (y0 - H)) * 96 + 3 * (zc & 31)) : ((yc - (y0 - H)) * ZP + zc);
-            op[j] = out + (size_t)b * 3 * N + ((uint32_t)xs * XS + (uint32_t)yc * Z + zc);
+            own_off[j] = IN_CL ? ((zc >> 5) * (ROWS * 96) + (yc - (r.y0 - H)) * 96 + 3 * (zc & 31)) : ((yc - (r.y0 - H)) * ZP + zc);
+            op[j] = out + (size_t)r.b * 3 * N + ((uint32_t)r.xs * XS + (uint32_t)yc * Z + zc);
         }
-        const float *const ring_end = ring + R * SLOT;
-        // planes needed by the first step
-        const int n0 = min(xs + H, p_last) - p_first;
-        for (int q = 0; q <= n0; ++q) mbar_wait_u(full_u + 8 * q, 0);
-        uint32_t wa = full_u + 8 * (n0 + 1), wph = 0;                  // next plane to wait for (n0 + 1 <= 2H + 1 < R)
-        int sb = xs - H - p_first;                                     // slot of plane x - H (in [-H, 0] at start)
+        int sb = rslot + (r.xs - H - r.p_first);                       // slot of plane xs - H (in [-H, 0] relative to the run)
         if (sb < 0) sb += R;
+        int sc = sb + H;
+        if (sc >= R) sc -= R;
         const float *pl = ring + sb * SLOT;                            // slot of plane x - H
-        const float *pc = ring + ((sb + H) % R) * SLOT;                // slot of plane x
+        const float *pc = ring + sc * SLOT;                            // slot of plane x
         uint32_t ea = empty_u + 8 * sb;
-        const int rel_x = p_first + H;                                 // first x whose plane x - H exists
-        int xmh1 = xs - H + 1;
-        float fx = (float)xs;
+        const int rel_x = r.p_first + H;                               // first x whose plane x - H belongs to the run
+        int xmh1 = r.xs - H + 1;
+        float fx = (float)r.xs;
+        int am = 0;                                                    // max |out| as float bits (NaN orders above +inf)
 
-        for (int x = xs; x < xe; ++x) {
-            if (x != xs && x + H <= p_last) {
+        for (int x = r.xs; x < r.xe; ++x) {
+            const int need = rq + min(x + H, r.p_last) - r.p_first;
+            while (wq <= need) {
                 mbar_wait_u(wa, wph);
-                wa += 8;
+                wa += 8; ++wq;
                 if (wa == full_u + 8 * R) { wa = full_u; wph ^= 1u; }
             }
 #if !DFM_EXACT_ORDER
@@ -199,8 +240,12 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     const u64_t y0 = fma2(pk(cyA, cyB), m1, pk((float)iyA, (float)iyB)), y1 = fma2(y0, m1, p1);
                     const u64_t z0 = fma2(pk(czA, czB), m1, pk((float)izA, (float)izB)), z1 = fma2(z0, m1, p1);
                     const u64_t w00 = mul2(x0, y0), w01 = mul2(x0, y1), w10 = mul2(x1, y0), w11 = mul2(x1, y1);
+#if MARCH_EXP == 3
+                    const u64_t w[8] = {x0, x0, x0, x0, x0, x0, x0, x0};
+#else
                     const u64_t w[8] = {mul2(w00, z0), mul2(w00, z1), mul2(w01, z0), mul2(w01, z1),
                                         mul2(w10, z0), mul2(w10, z1), mul2(w11, z0), mul2(w11, z1)};
+#endif
                     const float *qA0 = pl + dxA * SLOT, *qB0 = pl + dxB * SLOT;
                     if (qA0 >= ring_end) qA0 -= R * SLOT;
                     if (qB0 >= ring_end) qB0 -= R * SLOT;
@@ -225,12 +270,20 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     } else {
                         const int offA = ryA * ZP + (izA - 1), offB = ryB * ZP + (izB - 1);
                         qA0 += offA; qA1 += offA; qB0 += offB; qB1 += offB;
+#if MARCH_EXP == 1
+                        qA1 = qA0; qB1 = qB0;
+#endif
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
+#if MARCH_EXP == 2
+                            const float oa = c == 0 ? vA0 : c == 1 ? vA1 : vA2, ob = c == 0 ? vB0 : c == 1 ? vB1 : vB2;
+                            const float va[8] = {oa, oa, oa, oa, oa, oa, oa, oa}, vb[8] = {ob, ob, ob, ob, ob, ob, ob, ob};
+#else
                             const float va[8] = {qA0[c * CS], qA0[c * CS + 1], qA0[c * CS + ZP], qA0[c * CS + ZP + 1],
                                                  qA1[c * CS], qA1[c * CS + 1], qA1[c * CS + ZP], qA1[c * CS + ZP + 1]};
                             const float vb[8] = {qB0[c * CS], qB0[c * CS + 1], qB0[c * CS + ZP], qB0[c * CS + ZP + 1],
                                                  qB1[c * CS], qB1[c * CS + 1], qB1[c * CS + ZP], qB1[c * CS + ZP + 1]};
+#endif
                             acc[c] = mul2(w[0], pk(va[0], vb[0]));
 #pragma unroll
                             for (int k = 1; k < 8; ++k) acc[c] = fma2(w[k], pk(va[k], vb[k]), acc[c]);
@@ -293,6 +346,7 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                 } else {
                     // some lane's corners leave the ring: the whole warp gathers from global memory (same arithmetic)
                     const uint32_t lo = (uint32_t)(ax.i1 - 1) * GX + (uint32_t)(ay.i1 - 1) * GY + (uint32_t)(az.i1 - 1);
+                    const float *srcb = src + (size_t)r.b * 3 * N;
                     if (IN_CL) {
                         const float *g = srcb + 3 * (size_t)lo;
 #pragma unroll
@@ -330,8 +384,25 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
             ++xmh1;
             fx += 1.f;
         }
+        // end of the run: release its remaining planes max(xe - H, p_first) .. p_last
+        {
+            int p = r.xe - H;
+            while (p < r.p_first) { ++p; ea += 8; if (ea == empty_u + 8 * R) ea = empty_u; }
+            __syncwarp();
+            for (; p <= r.p_last; ++p) {
+                if (lane == 0) mbar_arrive_u(ea);
+                ea += 8;
+                if (ea == empty_u + 8 * R) ea = empty_u;
+            }
+        }
+        const int np = r.p_last - r.p_first + 1;
+        rq += np;
+        rslot = (rslot + np) % R;
+        if (FIRST && absmax) {
+            am = __reduce_max_sync(0xffffffffu, am);
+            if (lane == 0) atomicMax(reinterpret_cast<int *>(absmax) + r.b, am);
+        }
     }
-    if (FIRST && absmax) block_absmax_commit(__int_as_float(am), absmax + b);     // uniform branch, every thread arrives
 }
 
 // ------------------------------- host side -----------------------------------------------
@@ -357,9 +428,19 @@ static int launch_march_t(const float *src, float *out, int B, int X, int Y, int
         cudaFuncSetAttribute(k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
-    const int nseg = (X + seglen - 1) / seglen, nstrip = (Y + TY - 1) / TY;
-    dim3 grid(nseg, nstrip, B), block((TY / VPT * NZW + 1) * 32);
-    k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST><<<grid, block, smem, st>>>(tmap, src, out, X, Y, Z, scale, seglen, absmax, sel);
+    // persistent grid: every resident CTA slot gets one contiguous range of plane-steps (at least `seglen` of them)
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int nstrip = (Y + TY - 1) / TY;
+    const unsigned long long total = (unsigned long long)B * nstrip * X;
+    if (total >= (1ull << 32)) return DFM_EUNSUPPORTED;
+    const unsigned long long slots = (unsigned long long)sms * march_ctas(TY, H, R, NZW);
+    const unsigned grid = (unsigned)max(1ull, min(slots, total / (unsigned)max(seglen, 1)));
+    k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST><<<grid, (TY / VPT * NZW + 1) * 32, smem, st>>>(tmap, src, out, X, Y, Z, scale, nstrip, total, absmax, sel);
     return check_launch("k_ss_march");
 }
 
@@ -376,7 +457,7 @@ bool ss_march_eligible(const float *src, int X, int Y, int Z) {
     return !off && X >= 2 && Y >= 2 && Z >= 33 && Z <= 128 && Z % 4 == 0 && aligned16(src) && tma_planar_ok(src, X, Y, Z);
 }
 
-// variant 0: halo 2 (2 CTAs/SM); variant 1: halo 4 (1 CTA/SM) for the large displacements of the last steps.
+// variant 0: halo 2; variant 1: halo 3 (both 2 CTAs/SM at Z <= 96) for the large displacements of the last steps.
 // `first`: v = scale * src and max|out| per item goes to absmax (nullable); otherwise scale must be 1.
 int launch_ss_march(const float *src, float *out, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,
                     float *absmax, int variant, const float *sel, float sel_scale, float sel_thr, int sel_mode,
@@ -384,7 +465,7 @@ int launch_ss_march(const float *src, float *out, int B, int X, int Y, int Z, fl
     if (!ss_march_eligible(src, X, Y, Z)) return DFM_EUNSUPPORTED;
     if (!first && scale != 1.f) return DFM_EUNSUPPORTED;
     MarchSel ms = {sel, sel_scale, sel_thr, sel ? sel_mode : 0};
-    static const int seg0 = march_cfg_int("DFM_MARCH_SEG", 16), seg1 = march_cfg_int("DFM_MARCH_SEG_B", 20);
+    static const int seg0 = march_cfg_int("DFM_MARCH_SEG", 16), seg1 = march_cfg_int("DFM_MARCH_SEG_B", 16);   // minimum steps per CTA
     const int nzw = (Z + 31) / 32;
     // block size <= 1024 threads: TY * NZW + 1 <= 32 warps; ring bytes = R * 3 * (TY + 2H) * 32 NZW * 4 <= 227 KB
 #define DFM_MARCH(TYv, VPTv, Hv, Rv, NZWv, seg) \
@@ -408,7 +489,8 @@ int launch_ss_march(const float *src, float *out, int B, int X, int Y, int Z, fl
             if (cfgb == 1) DFM_MARCH(10, 1, 4, 10, 3, seg1);
             if (cfgb == 2) DFM_MARCH(8, 1, 3, 8, 3, seg1);
             if (cfgb == 3) DFM_MARCH(8, 2, 4, 10, 3, seg1);
-            DFM_MARCH(8, 1, 4, 10, 3, seg1);
+            if (cfgb == 4) DFM_MARCH(8, 1, 4, 10, 3, seg1);
+            DFM_MARCH(6, 2, 3, 8, 3, seg1);                  // halo 3 at 2 CTAs/SM beats halo 4 at 1 CTA/SM (0.1248 vs 0.1283 ms per step)
         default: DFM_MARCH(6, 1, 4, 10, 4, seg1);
     }
 #undef DFM_MARCH

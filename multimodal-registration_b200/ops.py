@@ -443,7 +443,9 @@ def rescale_warp(img, coarse_field, factor, fill_value=None):
     try:
         _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(None),
                   B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())
-    except _lib.DfmError:
+    except _lib.DfmError as e:
+        if e.code != _lib.DFM_EUNSUPPORTED:               # only "shape not covered by the fused kernel" falls back
+            raise
         work = torch.empty(B * 3 * X * Y * Z, device=img.device, dtype=torch.float32)
         _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(work),
                   B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())

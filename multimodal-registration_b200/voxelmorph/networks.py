@@ -174,13 +174,16 @@ class VxmDense(torch.nn.Module):
         s_out.wait_stream(cur)
         y_host = second_host = None
         second_is_input = False
-        alive = []
         for lo in range(0, B, batch_size):
             hi = min(lo + batch_size, B)
             with torch.cuda.stream(s_in):
                 src_d = src_p[lo:hi].to(dev, non_blocking=True)
                 flow_d = flow_p[lo:hi].to(dev, non_blocking=True)
             cur.wait_stream(s_in)
+            # chunk tensors are released as soon as the streams that use them have passed (record_stream), so
+            # device memory is O(batch_size), not O(B)
+            src_d.record_stream(cur)
+            flow_d.record_stream(cur)
             y, second = self.deform([src_d, flow_d], keep_pos_flow=keep)
             second_is_input = second is flow_d
             if y_host is None:
@@ -194,11 +197,12 @@ class VxmDense(torch.nn.Module):
                 y_host[lo:hi].copy_(y_c, non_blocking=True)
                 if sec_c is not None:
                     second_host[lo:hi].copy_(sec_c, non_blocking=True)
-            alive.append((src_d, flow_d, y, second, y_c, sec_c))
+            y_c.record_stream(s_out)
+            if sec_c is not None:
+                sec_c.record_stream(s_out)
         s_out.synchronize()
         cur.wait_stream(s_out)
         torch.cuda.current_stream().synchronize()
-        del alive
         y_np = y_host.numpy().copy() if copy else y_host.numpy()
         if second_is_input:
             sec_np = flow_h if isinstance(flow_h, np.ndarray) else flow_p.numpy()
