@@ -258,23 +258,62 @@ def run_own(args):
         e2e_ms = 1e3 * (time.perf_counter() - t0) / max(e2e_steps, 1)
         clocks = sampler.stop() if rank == 0 else None
 
-    ms = torch.tensor([total_ms / args.steps, e2e_ms] + stage_ms, device=dev, dtype=torch.float64)   # + ss, rescale, warp, fused
+        # ---- e2e ceiling: the step's host<->device bytes with NO kernels (one H2D stream, one D2H stream, every
+        # rank at once) -- what the PCIe / host-memory path of the box allows for this step ----
+        ceil_ms = page_ms = float('nan')
+        if not args.no_e2e:
+            d_svf, d_img = torch.empty_like(svf), torch.empty_like(img)
+            h_out = torch.empty(img.shape, dtype=torch.float32).pin_memory()
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def copy_only():
+                with torch.cuda.stream(s_up):
+                    d_svf.copy_(svf_pin, non_blocking=True)
+                    d_img.copy_(img_pin, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_out.copy_(d_img, non_blocking=True)
+            copy_only()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                copy_only()
+            barrier()
+            ceil_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+            del d_svf, d_img, h_out
+            # the pageable-numpy entry (what nibabel hands the reference: plain arrays in, fresh arrays out), once
+            if rank == 0:
+                svf_np, img_np = svf_h.numpy(), img_h.numpy()
+                model.predict_deform([img_np, svf_np], copy=True)
+                t0 = time.perf_counter()
+                model.predict_deform([img_np, svf_np], copy=True)
+                page_ms = 1e3 * (time.perf_counter() - t0)
+
+    ms = torch.tensor([total_ms / args.steps, e2e_ms, ceil_ms] + stage_ms, device=dev, dtype=torch.float64)   # + ss, rescale, warp, fused
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step, e2e_ms, ss_ms, rs_ms, wp_ms, fu_ms = [float(v) for v in ms.tolist()]
+    ms_per_step, e2e_ms, ceil_ms, ss_ms, rs_ms, wp_ms, fu_ms = [float(v) for v in ms.tolist()]
+
+    # ---- the other BASELINE.json configs (3: training-step tail incl. the NCCL all-reduce, 4: two-step cascade
+    # over 64 subjects, 5: Jacobian 256^3), every rank takes part; reported beside the headline ----
+    configs = None
+    if not (args.no_configs or args.no_e2e):
+        del svf, img, model
+        torch.cuda.empty_cache()
+        configs = run_configs(rank, world, dev)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         voxels = world * B * N_F
         kernels = {
-            'ss_step(k_ss_first_cl, k_ss_brick)': {'launches_per_step': INT_STEPS, 'ms_per_launch': ss_ms / INT_STEPS,
-                                    'algorithmic_bytes_per_launch': B * BYTES_SS_STEP, 'in_timed_region': True},
-            'rescale_x2(k_upsample3_march)': {'launches_per_step': 1, 'ms_per_launch': rs_ms,
-                                           'algorithmic_bytes_per_launch': B * BYTES_RESCALE, 'in_timed_region': True},
-            'warp_linear(k_warp_brick)': {'launches_per_step': 1, 'ms_per_launch': wp_ms,
-                                          'algorithmic_bytes_per_launch': B * BYTES_WARP, 'in_timed_region': True},
-            'rescale_warp_fused(k_warp_brick<fused>)': {'launches_per_step': 0, 'ms_per_launch': fu_ms,
-                                                        'algorithmic_bytes_per_launch': B * BYTES_FUSED, 'in_timed_region': False},
+            K_SS: {'launches_per_step': INT_STEPS, 'ms_per_launch': ss_ms / INT_STEPS,
+                   'algorithmic_bytes_per_launch': B * BYTES_SS_STEP, 'in_timed_region': True,
+                   'note': 'average of the 7 steps; steps 6 and 7 launch a halo-2 and a halo-3 variant, the one not selected per item exits'},
+            K_RS: {'launches_per_step': 1, 'ms_per_launch': rs_ms,
+                   'algorithmic_bytes_per_launch': B * BYTES_RESCALE, 'in_timed_region': True},
+            K_WP: {'launches_per_step': 1, 'ms_per_launch': wp_ms,
+                   'algorithmic_bytes_per_launch': B * BYTES_WARP, 'in_timed_region': True},
+            K_FU: {'launches_per_step': 0, 'ms_per_launch': fu_ms,
+                   'algorithmic_bytes_per_launch': B * BYTES_FUSED, 'in_timed_region': False},
         }
         for k in kernels.values():
             k['achieved_gbs'] = k['algorithmic_bytes_per_launch'] / (k['ms_per_launch'] * 1e-3) / 1e9
@@ -295,12 +334,22 @@ def run_own(args):
                     'd2h_bytes_per_step': int(img_pin.numel() * 4),
                     'note': 'chunked 3-stream pipeline (batch_size 2); the second output (pre-integration flow) is the '
                             'untouched input and is returned from the host copy, not re-downloaded',
+                    'ceiling_ms_per_step': ceil_ms, 'ceiling_value': voxels / (ceil_ms * 1e-3),
+                    'ceiling_gbs': {'h2d': world * (svf_pin.numel() + img_pin.numel()) * 4 / (ceil_ms * 1e-3) / 1e9,
+                                    'd2h': world * img_pin.numel() * 4 / (ceil_ms * 1e-3) / 1e9},
+                    'frac_of_ceiling': ceil_ms / e2e_ms,
+                    'ceiling_note': 'copy-only probe: the same H2D + D2H bytes per step on two streams, no kernels, all ranks at once '
+                                    '(aggregate GB/s over the ranks)',
+                    'pageable_ms_per_step': page_ms,
+                    'pageable_note': 'rank 0 alone, plain (pageable) numpy arrays in, fresh numpy arrays out (copy=True): adds a host '
+                                     'memcpy into / out of the pinned staging buffers',
                     'api': 'voxelmorph.networks.VxmDense(...).predict_deform([source, flow]) on pinned host arrays'},
             'gpu_launches': args.steps * (INT_STEPS + 2),
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': dom['achieved_gbs'], 'peak': peak,
                          'unit': 'GB/s', 'frac': dom['frac_of_peak'],
-                         'traffic': (TRAFFIC_NCU_PER_PAIR[dom_name] * B / 1e9) if dom_name in TRAFFIC_NCU_PER_PAIR else None,
-                         'traffic_unit': 'GB per launch (ncu dram read+write at B=8, scaled to this batch)',
+                         'traffic': TRAFFIC_NCU_B32_GB.get(dom_name) if B == 32 else None,
+                         'traffic_unit': 'GB per launch: dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full '
+                                         'capture of THIS command at B=32 (profiles/r2_b32_ncu_full_summary.csv)',
                          'achieved_bytes_per_launch_GB': dom['algorithmic_bytes_per_launch'] / 1e9,
                          'peak_source': peak_src,
                          'pipeline_achieved': B * (INT_STEPS * BYTES_SS_STEP + BYTES_RESCALE + BYTES_WARP)
@@ -310,19 +359,46 @@ def run_own(args):
                              'sample': '%d volume pairs of the same workload (%.1f s), restated reference '
                                        '(oracle/torch_oracle.py, torch-CPU fp32, %d threads)' % (n_cpu, cpu_s, cores)},
             'clocks': clocks,
+            'configs': configs,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch PER VOLUME PAIR, from the committed
-# `ncu --set full` capture at B=8 (profiles/r1_final_ncu_full_summary.csv); scaled by the batch.
-TRAFFIC_NCU_PER_PAIR = {
-    'ss_step(k_ss_first_cl, k_ss_brick)': (59.009e6 + 22.149e6) / 8,
-    'rescale_x2(k_upsample3_march)': (62.984e6 + 415.512e6) / 8,
-    'warp_linear(k_warp_brick)': (629.240e6 + 144.899e6) / 8,
+K_SS = 'ss_step(k_ss_march)'
+K_RS = 'rescale_x2(k_upsample3_march)'
+K_WP = 'warp_linear(k_warp_brick_var)'
+K_FU = 'rescale_warp_fused(k_warp_brick<fused>)'
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of
+# `python bench.py --steps 2 --warmup 3 --batch 32 --no-e2e` (profiles/r2_b32_ncu_full_summary.csv; the SS entry is
+# a halo-2 step).  Every kernel moves slightly LESS than its algorithmic bytes: part of the writes is still in the
+# 126 MB L2 when the launch ends.
+TRAFFIC_NCU_B32_GB = {
+    K_SS: 0.25637 + 0.19567,
+    K_RS: 0.25414 + 1.82949,
+    K_WP: 2.51661 + 0.61712,
 }
+
+
+def run_configs(rank, world, dev):
+    """BASELINE.json configs 3-5 through the scripts that measure them (same code as the stand-alone runs)."""
+    import importlib.util
+    import torch
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'scripts', name + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    out = {}
+    out['config3_train_step_tail'] = load('bench_train_tail').measure(rank, world, dev, items=2, steps=5, warmup=3)
+    torch.cuda.empty_cache()
+    out['config4_two_step_64_subjects'] = load('bench_two_step').measure(rank, world, dev, subjects=64, steps=3, warmup=2)
+    torch.cuda.empty_cache()
+    out['config5_jacobian_256'] = load('bench_jacobian').measure(rank, world, dev, fields=8, steps=5, warmup=3)
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -333,6 +409,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32, help='volume pairs per GPU per step')
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e and cpu_baseline legs (profiling runs)')
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3-5 (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -77,6 +77,15 @@ int dfm_warp_fwd(const void *img, const float *field, void *out,
                  int interp, int elem_size, int has_fill, float fill, uint64_t fill_bits,
                  unsigned flags, void *stream);
 
+/* Channel-wise vxm.utils.transform [UR] (train_synthmorph.py:61-67, generate_label_maps): every channel of a
+ * channels-last volume moves by its own 3-vector field, both tensors in the reference's layout, no transposes.
+ *   vol [B][Xi][Yi][Zi][C], shift [B][X][Y][Z][C][3] -> out[b,p,c] = interp(vol[b,...,c], p + shift[b,p,c,:])
+ *   (linear, edge clamp, optional fill as in dfm_warp_fwd).  argmax = 0: out is float [B][X][Y][Z][C];
+ *   argmax = 1 (C <= 256): the tf.argmax(im, axis=-1) that follows at train_synthmorph.py:68 is taken in the
+ *   kernel (first maximum) and out is uint8 [B][X][Y][Z].  DFM_EUNSUPPORTED when X*Y*Z*C*C >= 2^32. */
+int dfm_warp_channelwise_fwd(const float *vol, const float *shift, void *out, int B, int C, int Xi, int Yi, int Zi,
+                             int X, int Y, int Z, int has_fill, float fill, int argmax, void *stream);
+
 /* Fused RescaleTransform(factor >= 1) + linear SpatialTransformer of a one-channel image: the
  * deformation tail of VxmDense at inference (3d_reg.py:305,310; bids_*.py:311-322), where the
  * full-resolution warp is only an intermediate.  out[b,p] = interp(img[b], p + U[b,:,p]) with
@@ -238,6 +247,26 @@ int dfm_warp_dice_bwd(const float *y_true, const float *coef, const float *img, 
  * ------------------------------------------------------------------------------------- */
 int dfm_cl_to_planar(const void *cl, void *planar, int B, int C, size_t N, int elem_size, void *stream);
 int dfm_planar_to_cl(const void *planar, void *cl, int B, int C, size_t N, int elem_size, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Voxel-level evaluation metrics.  Inputs are float32 (is_f64 = 0) or float64
+ * (is_f64 = 1, what nibabel's get_fdata() hands the reference scripts) device arrays of n elements.
+ *   dfm_minmax       out2 = {min, max};  work: dfm_metrics_workspace_bytes() of scratch.
+ *   dfm_joint_hist   replaces np.histogramdd([a, b], bins) of normalized_mutual_information
+ *                    (eval_reg_with_mi.py:66-69): edges np.linspace(min, max, bins + 1) per image in float64,
+ *                    right-most edge inclusive; hist [bins][bins] uint64 (row = bin of a), overwritten.
+ *                    minmax_a / minmax_b: DEVICE {min, max} pairs from dfm_minmax (no host round trip).
+ *   dfm_axis_sums    the three plane sums of detect_zero_padding (eval_reg_with_mi.py:16-36):
+ *                    xs[x] = sum_{y,z}, ys[y] = sum_{x,z}, zs[z] = sum_{x,y}, float64, overwritten.
+ *   dfm_overlap_sums the masked sums of eval_reg_on_sc_seg.py:80-93: out5 = {sum(m[fx == 1]), sum(m[fx == 0]),
+ *                    count(fx == 1), count(fx == 0), sum(m)} in float64; work as for dfm_minmax.
+ * ------------------------------------------------------------------------------------- */
+size_t dfm_metrics_workspace_bytes(void);
+int dfm_minmax(const void *a, size_t n, int is_f64, double *out2, double *work, void *stream);
+int dfm_joint_hist(const void *a, const void *b, size_t n, int is_f64, const double *minmax_a, const double *minmax_b,
+                   int bins, unsigned long long *hist, void *stream);
+int dfm_axis_sums(const void *im, int X, int Y, int Z, int is_f64, double *xs, double *ys, double *zs, void *stream);
+int dfm_overlap_sums(const void *fx, const void *m, size_t n, int is_f64, double *out5, double *work, void *stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ neurite API used by ivadomed/multimodal-registration.
               rescale_dense_transform/integrate_vec, networks.Transform/VxmDense, py.utils)
   neurite     mirror of neurite.utils.interpn/resize/zoom and utils.augment.draw_perlin
   sct_warp    the SCT warp-file convention of 3d_reg.py:390-422 (rescale, RAI components, intent 1007)
+  metrics     NMI joint histogram, zero-padding box and segmentation-overlap metrics of the eval scripts
   pipelines   device-resident tails of the registration scripts (two-step cascade, sub-volume stitching, export)
 
 The directory name is not a Python identifier; import it through the top-level alias module
@@ -19,6 +20,7 @@ from . import _lib, ops, sharding          # noqa: F401
 from . import neurite, voxelmorph   # noqa: F401
 from . import sct_warp             # noqa: F401
 from . import pipelines            # noqa: F401
+from . import metrics              # noqa: F401
 
 __version__ = '0.1.0'
 

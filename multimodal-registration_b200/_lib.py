@@ -23,6 +23,7 @@ SIGNATURES = {
     'dfm_exact_order': (_i, []),
     'dfm_last_error': (_c.c_char_p, []),
     'dfm_warp_fwd': (_i, [_p, _p, _p] + [_i] * 8 + [_i, _i, _i, _f, _u64, _u, _p]),
+    'dfm_warp_channelwise_fwd': (_i, [_p, _p, _p] + [_i] * 9 + [_f, _i, _p]),
     'dfm_rescale_warp_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _f, _p]),
     'dfm_warp_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
     'dfm_field_warp_add': (_i, [_p, _p, _p] + [_i] * 7 + [_f, _i, _u, _p]),
@@ -42,6 +43,11 @@ SIGNATURES = {
     'dfm_grad_l2_workspace_bytes': (_z, [_i] * 4),
     'dfm_grad_l2_sums': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),
     'dfm_grad_l2_bwd': (_i, [_p, _p, _p] + [_i] * 4 + [_u, _p]),
+    'dfm_metrics_workspace_bytes': (_z, []),
+    'dfm_minmax': (_i, [_p, _z, _i, _p, _p, _p]),
+    'dfm_joint_hist': (_i, [_p, _p, _z, _i, _p, _p, _i, _p, _p]),
+    'dfm_axis_sums': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    'dfm_overlap_sums': (_i, [_p, _p, _z, _i, _p, _p, _p]),
     'dfm_cl_to_planar': (_i, [_p, _p, _i, _i, _z, _i, _p]),
     'dfm_planar_to_cl': (_i, [_p, _p, _i, _i, _z, _i, _p]),
 }

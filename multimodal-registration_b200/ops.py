@@ -219,22 +219,39 @@ def warp(img, field, interp_method=LINEAR, fill_value=None, loc_absolute=False):
     return _warp_fwd_raw(img.detach(), field.detach(), NEAREST, fill_value, loc_absolute)
 
 
-def warp_channelwise(img, field, interp_method=LINEAR, fill_value=None):
+def warp_channelwise(img, field, interp_method=LINEAR, fill_value=None, argmax=False):
     """Channel-wise transform: field [B, X, Y, Z, C, 3] carries one 3-vector per channel
-    (``vxm.utils.transform`` as called at train_synthmorph.py:67).  Each channel is an
-    independent single-channel warp, so this is the batched kernel over B*C items."""
+    (``vxm.utils.transform`` as called at train_synthmorph.py:67).  Linear interpolation runs one kernel that
+    addresses both tensors in the reference's channels-last layout (dfm.h: dfm_warp_channelwise_fwd);
+    ``argmax=True`` also takes the ``tf.argmax(im, axis=-1)`` that follows at :68 inside the kernel and returns
+    the uint8 label map [B, X, Y, Z].  Nearest interpolation (and volumes past the kernel's 32-bit index range)
+    run as B*C one-channel warps."""
     _require_cuda(img, 'img')
     _require_cuda(field, 'field')
+    if field.dim() != 6 or img.dim() != 5:
+        raise ValueError('channel-wise transform: img [B, X, Y, Z, C], field [B, X, Y, Z, C, 3]')
     B, X, Y, Z, C, D = field.shape
-    if D != 3 or img.shape[-1] != C:
+    if D != 3 or img.shape[-1] != C or img.shape[0] != B:
         raise ValueError('channel-wise field must be [B, X, Y, Z, C, 3] with C == img channels')
-    img_p = to_layout(img, 'planar')                         # storage [B, C, Xi, Yi, Zi]
     Xi, Yi, Zi = img.shape[1:4]
+    if _interp_code(interp_method) == _lib.DFM_LINEAR:
+        vol = img.detach().float().contiguous()                 # channels-last storage
+        shift = field.detach().float().contiguous()
+        out = torch.empty((B, X, Y, Z) if argmax else (B, X, Y, Z, C), device=img.device,
+                          dtype=torch.uint8 if argmax else torch.float32)
+        try:
+            _lib.call('dfm_warp_channelwise_fwd', _ptr(vol), _ptr(shift), _ptr(out), B, C, Xi, Yi, Zi, X, Y, Z,
+                      int(fill_value is not None), float(fill_value or 0.0), int(bool(argmax)), _stream())
+            return out
+        except _lib.DfmError as e:
+            if e.code != _lib.DFM_EUNSUPPORTED:
+                raise
+    img_p = to_layout(img, 'planar')                         # storage [B, C, Xi, Yi, Zi]
     img_items = img_p.permute(0, 4, 1, 2, 3).reshape(B * C, Xi, Yi, Zi, 1)
-    f = to_layout(field.reshape(B, X, Y, Z, C * 3).float(), 'planar')        # [B, C*3, X, Y, Z]
-    f_items = f.permute(0, 4, 1, 2, 3).reshape(B * C, 3, X, Y, Z).permute(0, 2, 3, 4, 1)
+    f_items = field.float().permute(0, 4, 5, 1, 2, 3).contiguous().reshape(B * C, 3, X, Y, Z).permute(0, 2, 3, 4, 1)   # planar items
     out = warp(img_items, f_items, interp_method, fill_value)               # [B*C, X, Y, Z, 1]
-    return out.reshape(B, C, X, Y, Z).permute(0, 2, 3, 4, 1)
+    out = out.reshape(B, C, X, Y, Z).permute(0, 2, 3, 4, 1)
+    return out.argmax(-1).to(torch.uint8) if argmax else out
 
 
 # ---------------------------------------------------------------------------------------

@@ -203,10 +203,10 @@ class VxmDense(torch.nn.Module):
         s_out.synchronize()
         cur.wait_stream(s_out)
         torch.cuda.current_stream().synchronize()
-        y_np = y_host.numpy().copy() if copy else y_host.numpy()
+        y_np = _host.host_copy(y_host) if copy else y_host.numpy()
         if second_is_input:
             sec_np = flow_h if isinstance(flow_h, np.ndarray) else flow_p.numpy()
             sec_np = np.asarray(sec_np, dtype=np.float32)
         else:
-            sec_np = second_host.numpy().copy() if copy else second_host.numpy()
+            sec_np = _host.host_copy(second_host) if copy else second_host.numpy()
         return [y_np, sec_np]

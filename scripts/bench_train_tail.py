@@ -41,19 +41,10 @@ FWD = 2 * (STEPS * 24 * N_H + 12 * N_H + 12 * N_F + 20 * N_F) + (12 * N_F + 12 *
 BWD = (8 * C + 24) * N_F + (12 * N_F + 12 * N_H) + STEPS * 36 * N_H + (12 * N_F + 12 * N_H)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--items', type=int, default=2, help='items per GPU per step')
-    ap.add_argument('--steps', type=int, default=5)
-    ap.add_argument('--warmup', type=int, default=3)
-    args = ap.parse_args()
-    rank, world = sharding.env_rank_world()
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    B = args.items
+def measure(rank, world, dev, items=2, steps=5, warmup=3):
+    """One process per GPU; the process group (if world > 1) is already initialised.  Returns the result dict
+    (identical on every rank: times are max over ranks)."""
+    B = items
     g = torch.Generator(device='cpu').manual_seed(100 + rank)
 
     def smooth(shape_c, std):
@@ -89,31 +80,47 @@ def main():
         sharding.allreduce_mean_(unet_grad)                       # the step's only collective
         return flow.grad, y_source
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     t1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev, dtype=torch.float64)
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    peak, src = bench.measured_peak_gbs()
+    ms = float(ms.item())
+    gbs = world * B * (FWD + BWD) / (ms * 1e-3) / 1e9
+    return {'workload': 'train_synthmorph.py step, deformation hot path fwd+bwd (config/config.json shapes)',
+            'n_gpus': world, 'items_per_gpu': B, 'ms_per_step': ms, 'items_per_s': world * B / (ms * 1e-3),
+            'algorithmic_GB_per_item': (FWD + BWD) / 1e9, 'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak,
+            'includes': '26-channel map and its gradient in the reference channels-last layout (no conversion), 5.79 MB NCCL all-reduce',
+            'scaling': 'weak'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--items', type=int, default=2, help='items per GPU per step')
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    args = ap.parse_args()
+    rank, world = sharding.env_rank_world()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    res = measure(rank, world, dev, args.items, args.steps, args.warmup)
     if rank == 0:
-        peak, src = bench.measured_peak_gbs()
-        ms = float(ms.item())
-        gbs = world * B * (FWD + BWD) / (ms * 1e-3) / 1e9
-        print(json.dumps({'workload': 'train_synthmorph.py step, deformation hot path fwd+bwd (config/config.json shapes)',
-                          'n_gpus': world, 'items_per_gpu': B, 'ms_per_step': ms, 'items_per_s': world * B / (ms * 1e-3),
-                          'algorithmic_GB_per_item': (FWD + BWD) / 1e9, 'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak,
-                          'includes': '26-channel map and its gradient in the reference channels-last layout (no conversion), 5.79 MB all-reduce',
-                          'scaling': 'weak'}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 

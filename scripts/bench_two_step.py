@@ -26,9 +26,66 @@ from multimodal_registration_b200 import ops, sharding
 
 FULL, HALF = bench.FULL, bench.HALF
 N_F, N_H = bench.N_F, bench.N_H
-# algorithmic bytes per subject: compose (36 B/voxel half-res) + rescale x2 + linear warp + nearest warp
-# + rescale x2 for the saved warp
-BYTES = 36 * N_H + (12 * N_H + 12 * N_F) + 20 * N_F + 20 * N_F + (12 * N_H + 12 * N_F)
+INT_STEPS = 7
+# algorithmic bytes per subject: two VxmDense tails (7 SS steps + x2 rescale + linear warp each),
+# compose at half resolution, Transform(nearest, rescale=2) of a segmentation with the composed warp, x2 rescale
+# of the saved SCT warp
+TAIL = INT_STEPS * 24 * N_H + (12 * N_H + 12 * N_F) + 20 * N_F
+BYTES = 2 * TAIL + 36 * N_H + ((12 * N_H + 12 * N_F) + 20 * N_F) + (12 * N_H + 12 * N_F)
+
+
+def measure(rank, world, dev, subjects=64, steps=5, warmup=3):
+    """One process per GPU; the process group (if world > 1) is already initialised.  Subjects are sharded
+    across ranks (strong scaling: the 64-subject set is fixed); times are max over ranks.  Everything runs through
+    pipelines.two_steps_tail -- the device-resident restatement of bids_two_steps_registration.py:316-355,504-516."""
+    from multimodal_registration_b200 import pipelines
+    from multimodal_registration_b200.voxelmorph import networks
+    mine = sharding.shard_items(subjects, rank, world)
+    B = len(mine)
+    g = torch.Generator(device='cpu').manual_seed(7 + rank)
+
+    def field(std):
+        c = torch.randn(B, 3, 10, 10, 12, generator=g) * std
+        return torch.nn.functional.interpolate(c, size=HALF, mode='trilinear', align_corners=True).permute(0, 2, 3, 4, 1).contiguous().to(dev)
+
+    flow1, flow2 = field(3.0), field(1.0)                             # what the two U-Nets' flow convolutions emit
+    moving = torch.rand(B, *FULL, 1, generator=g).to(dev)
+    fixed = torch.rand(B, *FULL, 1, generator=g).to(dev)
+    seg = torch.randint(0, 26, (B, *FULL, 1), generator=g).float().to(dev)
+    model1 = networks.VxmDense(FULL, int_steps=INT_STEPS, svf_resolution=2, int_resolution=2)
+    model2 = networks.VxmDense(FULL, int_steps=INT_STEPS, svf_resolution=2, int_resolution=2)
+    tr_seg = networks.Transform(FULL, interp_method='nearest', rescale=2)
+
+    def step():
+        with torch.no_grad():
+            res = pipelines.two_steps_tail(moving, fixed, model1, model2, flow1, flow2, 'linear')    # :316-324
+            moved_seg = tr_seg([seg, res['warp']])                    # nearest variant of the final transform (:338-355)
+            saved = ops.rescale_dense_transform(res['warp'], res['scale'], out_layout='cl')          # :515
+        return res['moved'], moved_seg, saved
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    peak, _ = bench.measured_peak_gbs()
+    ms = float(ms.item())
+    gbs = subjects * BYTES / (ms * 1e-3) / 1e9
+    return {'workload': 'bids_two_steps_registration.py via pipelines.two_steps_tail: two VxmDense tails (7 SS steps, x2, linear warp), compose, nearest seg transform, x2 rescale of the saved warp, per subject',
+            'n_gpus': world, 'subjects': subjects, 'subjects_per_gpu': B, 'ms_per_pass': ms,
+            'subjects_per_s': subjects / (ms * 1e-3), 'algorithmic_GB_per_subject': BYTES / 1e9,
+            'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak, 'scaling': 'strong'}
 
 
 def main():
@@ -43,51 +100,9 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    mine = sharding.shard_items(args.subjects, rank, world)
-    B = len(mine)
-    g = torch.Generator(device='cpu').manual_seed(7 + rank)
-
-    def field(std):
-        c = torch.randn(B, 3, 10, 10, 12, generator=g) * std
-        return torch.nn.functional.interpolate(c, size=HALF, mode='trilinear', align_corners=True).permute(0, 2, 3, 4, 1).contiguous().to(dev)
-
-    w1, w2 = field(3.0), field(1.0)
-    moving = torch.rand(B, *FULL, 1, generator=g).to(dev)
-    seg = torch.randint(0, 26, (B, *FULL, 1), generator=g).float().to(dev)
-
-    def step():
-        with torch.no_grad():
-            warp = ops.compose([w1, w2])                              # :324
-            full = ops.rescale_dense_transform(warp, 2)               # Transform(rescale=2) / :515
-            moved = ops.warp(moving, full)                            # linear image warp
-            moved_seg = ops.warp(seg, full, 'nearest')                # nearest variant (:338-355)
-            saved = ops.rescale_dense_transform(warp, 2, out_layout='cl')
-        return moved, moved_seg, saved
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        step()
-    t1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    res = measure(rank, world, dev, args.subjects, args.steps, args.warmup)
     if rank == 0:
-        peak, _ = bench.measured_peak_gbs()
-        ms = float(ms.item())
-        gbs = args.subjects * BYTES / (ms * 1e-3) / 1e9
-        print(json.dumps({'workload': 'bids_two_steps_registration.py: compose + x2 rescale + linear and nearest warp per subject',
-                          'n_gpus': world, 'subjects': args.subjects, 'subjects_per_gpu': B, 'ms_per_pass': ms,
-                          'subjects_per_s': args.subjects / (ms * 1e-3), 'algorithmic_GB_per_subject': BYTES / 1e9,
-                          'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak, 'scaling': 'strong'}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 

@@ -143,15 +143,43 @@ def test_identity_and_translation_known_answers():
     np.testing.assert_array_equal(got, img[:, :, np.clip(np.arange(8) + 3, 0, 7)])
 
 
-def test_transform_channelwise():
+@pytest.mark.parametrize('shape', [(6, 8, 12, 4), (5, 7, 9, 26), (4, 3, 5, 33), (9, 4, 6, 1)])
+def test_transform_channelwise(shape):
+    """train_synthmorph.py:67 -- k_warp_cw addresses [X,Y,Z,C] / [X,Y,Z,C,3] in place; the oracle runs the
+    reference's 4-D interpn (16 corners, integral channel coordinate)."""
     rng = np.random.default_rng(9)
-    X, Y, Z, C = 6, 8, 12, 4
+    X, Y, Z, C = shape
     vol = rng.random((X, Y, Z, C)).astype(np.float32)
     shift = smooth_noise(rng, (X, Y, Z, C, 3), 2.0, smooth=0)
     want = io.transform(vol, shift)
     got = vxm.utils.transform(vol, shift)
     assert tuple(got.shape) == (X, Y, Z, C)
-    assert_linear_parity(host(got[None])[0], want)
+    assert_linear_parity(got.cpu().numpy(), want)
+    want_fill = io.transform(vol, shift, fill_value=-1.0)
+    assert_linear_parity(vxm.utils.transform(vol, shift, fill_value=-1.0).cpu().numpy(), want_fill)
+    # nearest takes the per-channel path
+    np.testing.assert_array_equal(vxm.utils.transform(vol, shift, 'nearest').cpu().numpy(), io.transform(vol, shift, 'nearest'))
+    # batched call + the fused tf.argmax of train_synthmorph.py:68 (first maximum)
+    vol_b = np.stack([vol, vol[::-1].copy()])
+    shift_b = np.stack([shift, -shift])
+    got_b = ops.warp_channelwise(dev(vol_b), torch.from_numpy(shift_b).cuda())
+    assert_linear_parity(got_b[0].cpu().numpy(), want)
+    assert_linear_parity(got_b[1].cpu().numpy(), io.transform(vol_b[1], shift_b[1]))
+    if C <= 256:
+        lab = ops.warp_channelwise(dev(vol_b), torch.from_numpy(shift_b).cuda(), argmax=True)
+        assert lab.dtype == torch.uint8 and tuple(lab.shape) == (2, X, Y, Z)
+        np.testing.assert_array_equal(lab.cpu().numpy(), got_b.argmax(-1).cpu().numpy().astype(np.uint8))   # same values -> same argmax
+
+
+def test_channelwise_argmax_ties_go_to_the_first_channel():
+    vol = np.zeros((4, 4, 4, 5), np.float32)
+    vol[..., 1] = 1.0
+    vol[..., 3] = 1.0                                         # channels 1 and 3 tie everywhere
+    shift = np.zeros((4, 4, 4, 5, 3), np.float32)
+    lab = ops.warp_channelwise(dev(vol[None]), torch.from_numpy(shift[None]).cuda(), argmax=True)
+    assert (lab.cpu().numpy() == 1).all()
+    lab0 = ops.warp_channelwise(dev(np.zeros_like(vol)[None]), torch.from_numpy(shift[None]).cuda(), argmax=True)
+    assert (lab0.cpu().numpy() == 0).all()
 
 
 def test_interpn_absolute_locations():
