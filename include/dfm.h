@@ -138,8 +138,9 @@ size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nsteps, int sa
 int dfm_vecint_fwd(const float *svf, float *out, float *work,
                    int B, int X, int Y, int Z, int nsteps, int save_steps,
                    unsigned flags, void *stream);
-/* gsvf = d loss / d svf given gout = d loss / d out and the saved steps (planar).
- * `scratch`: 2 * B*3*X*Y*Z floats.  All tensors planar. */
+/* gsvf = d loss / d svf given gout = d loss / d out and `saved` = the workspace dfm_vecint_fwd filled with
+ * save_steps != 0 (the step inputs AND the trailing B-float displacement bound, which selects per item between the
+ * atomics-free gather adjoint and the scatter adjoint of each step).  `scratch`: 2 * B*3*X*Y*Z floats.  All planar. */
 int dfm_vecint_bwd(const float *gout, const float *saved, float *gsvf, float *scratch,
                    int B, int X, int Y, int Z, int nsteps, void *stream);
 
@@ -148,6 +149,11 @@ int dfm_vecint_bwd(const float *gout, const float *saved, float *gsvf, float *sc
  * (so gv must not alias g).  Exposed for tests. */
 int dfm_ss_step_bwd(const float *g, const float *v, float *gv,
                     int B, int X, int Y, int Z, float scale, void *stream);
+/* The same with a displacement bound: item b satisfies |v| <= bound[b] * bscale (device array of B floats).  Items
+ * bounded below one voxel take the gather formulation of the volume path (no atomics, deterministic); the others
+ * scatter with red.global.add.  dfm_ss_step_bwd is this call without a bound. */
+int dfm_ss_step_bwd_bounded(const float *g, const float *v, float *gv, const float *bound, float bscale,
+                            int B, int X, int Y, int Z, float scale, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * RescaleTransform(zoom) -> vxm.utils.rescale_dense_transform -> ne.utils.resize [UR]

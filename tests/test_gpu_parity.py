@@ -511,6 +511,51 @@ def test_vecint_backward(nsteps):
     np.testing.assert_allclose(host(ts.grad), gs, rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('shape', [(6, 8, 10), (19, 5, 33), (20, 12, 96), (6, 5, 130)])
+@pytest.mark.parametrize('std', [0.3, 6.0, 40.0])
+def test_vecint_backward_gather_and_scatter_items(shape, std):
+    """Per-item selection between the atomics-free gather adjoint (|v| < 1: early steps) and the scatter adjoint:
+    item 1 moves 40x less than item 0, so the two take different kernels in the same launch; segment / strip / z edges
+    (shapes that are no multiples of the tile), Z > 128 (scatter only)."""
+    rng = np.random.default_rng(shape[0] * 7 + int(std))
+    svf = smooth_noise(rng, (2,) + shape + (3,), std).astype(np.float64)
+    svf[1] *= 0.025
+    nsteps = 5
+    g, (gs,) = _grads_oracle(lambda s: to.vec_int(s, nsteps), svf)
+    ts = dev(svf.astype(np.float32)).requires_grad_(True)
+    ops.vecint(ts, nsteps).backward(dev(g, 'cl'))
+    scale = max(1.0, float(np.abs(gs).max()))
+    # a sample that lands within an ulp of a cell boundary picks the other cell in fp32 than in the fp64 oracle, and the
+    # gradient is discontinuous there: tolerate a handful of such voxels
+    bad = ~np.isclose(host(ts.grad), gs, rtol=5e-4, atol=5e-5 * scale)
+    assert bad.sum() <= max(3, 2e-3 * bad.size), (bad.sum(), bad.size)
+
+
+def test_ss_step_bwd_gather_equals_scatter():
+    """dfm_ss_step_bwd_bounded with a bound below one voxel (gather kernel, no atomics) against the same call without
+    a bound (scatter kernel): same gradient up to summation order; the gather result is bit-reproducible."""
+    from multimodal_registration_b200.ops import _ptr, _stream
+    rng = np.random.default_rng(77)
+    B, X, Y, Z = 3, 21, 14, 40
+    v = (smooth_noise(rng, (B, X, Y, Z, 3), 0.18)).astype(np.float32)
+    v[2] *= 9.0                                                 # item 2 exceeds the bound -> scatter path
+    tv = dev(v, 'planar')
+    tg = dev(rng.standard_normal((B, X, Y, Z, 3)).astype(np.float32), 'planar')
+    bound = torch.tensor([float(np.abs(v[b]).max()) for b in range(B)], device='cuda')
+    assert bound[0] < 1 and bound[1] < 1 and bound[2] > 1
+    outs = []
+    for use_bound in (False, True, True):
+        gv = ops.empty((B, X, Y, Z, 3), 'planar', tv.device)
+        gv.fill_(float('nan'))                                  # the call must overwrite / zero everything itself
+        if use_bound:
+            mrb._lib.call('dfm_ss_step_bwd_bounded', _ptr(tg), _ptr(tv), _ptr(gv), _ptr(bound), 1.0, B, X, Y, Z, 0.5, _stream())
+        else:
+            mrb._lib.call('dfm_ss_step_bwd', _ptr(tg), _ptr(tv), _ptr(gv), B, X, Y, Z, 0.5, _stream())
+        outs.append(host(gv))
+    np.testing.assert_allclose(outs[1], outs[0], rtol=2e-5, atol=2e-5)
+    np.testing.assert_array_equal(outs[1][:2], outs[2][:2])     # gather items: deterministic
+
+
 @pytest.mark.parametrize('factor', [2, 0.5, 1.5])
 def test_rescale_backward_and_adjointness(factor):
     rng = np.random.default_rng(47)

@@ -108,3 +108,55 @@ def test_two_steps_subvolumes_linear():
     assert res['scale'] == 2
     check(res['warp'], stitched[None].astype(np.float32))
     check(res['moved'], moved)
+
+
+@pytest.mark.parametrize('interp', ['linear', 'nearest'])
+def test_bids_two_steps_registration_script(tmp_path, interp, arithmetic_mode):
+    """scripts/bids_two_steps_registration.py end to end (NIfTI + flow files in, moved image + SCT warp out, the
+    reference's file names) against the chained oracle."""
+    import json
+    import os
+    import runpy
+    from multimodal_registration_b200 import _nifti
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(11)
+    full, half = (16, 32, 48), (8, 16, 24)
+    moving = rng.random(full).astype(np.float32)
+    fixed = rng.random(full).astype(np.float32)
+    if interp == 'nearest':
+        moving = np.floor(moving * 4).astype(np.float32)
+    flow1 = smooth(rng, (1,) + half + (3,), 1.2)[0]
+    flow2 = smooth(rng, (1,) + half + (3,), 0.6)[0]
+    affine = np.array([[0, 0, 2.0, -10], [-1.5, 0, 0, 4], [0, 1.0, 0, 7], [0, 0, 0, 1]])      # a permuted, flipped orientation
+    mp, fp = str(tmp_path / 'sub-03_T2w_proc.nii.gz'), str(tmp_path / 'sub-03_T1w_proc.nii.gz')
+    _nifti.save_nifti(moving, mp, affine)
+    _nifti.save_nifti(fixed, fp, affine)
+    np.save(str(tmp_path / 'flow1.npy'), flow1)
+    _nifti.save_nifti(flow2[:, :, :, None, :], str(tmp_path / 'flow2.nii.gz'), affine, intent_code=1007)
+    cfg = json.load(open(os.path.join(root, 'config', 'config_inference.json')))
+    cfg['warp_interpolation'] = interp
+    json.dump(cfg, open(str(tmp_path / 'cfg.json'), 'w'))
+    mod = runpy.run_path(os.path.join(root, 'scripts', 'bids_two_steps_registration.py'))
+    assert mod['main'](['--model1-path', str(tmp_path / 'flow1.npy'), '--model2-path', str(tmp_path / 'flow2.nii.gz'),
+                        '--config-path', str(tmp_path / 'cfg.json'), '--fx-img-path', fp, '--mov-img-path', mp,
+                        '--fx-img-contrast', 'T1w']) == 0
+    moved, aff2 = _nifti.load_nifti(str(tmp_path / 'sub-03_T2w_proc_reg_to_T1w.nii.gz'))
+    warp, _, hdr = _nifti.load_nifti(str(tmp_path / 'sub-03_T2w_proc_field_to_T1w.nii.gz'), return_header=True)
+    np.testing.assert_allclose(aff2, affine)
+    mv5 = moving[None, ..., None]
+    steps = cfg['int_steps']
+    if interp == 'linear':
+        moved_first, w1 = oracle_tail(mv5, flow1[None], steps)
+        want_moved, w2 = oracle_tail(moved_first, flow2[None], steps)
+        want_warp = io.compose([w1[0], w2[0]])
+    else:
+        _, w1 = oracle_tail(mv5, flow1[None], steps)
+        moved_first = io.transform_model(mv5, w1, interp, rescale=2)
+        _, w2 = oracle_tail(moved_first, flow2[None], steps)
+        want_warp = io.compose([w1[0], w2[0]])
+        want_moved = io.transform_model(mv5, want_warp[None], interp, rescale=2)
+    check(moved, want_moved[0, ..., 0])
+    axcodes = _nifti.aff2axcodes(-affine)
+    want_sct = sct_oracle.apply(io.rescale_dense_transform(want_warp[None], 2)[0], axcodes)
+    assert warp.shape == full + (1, 3) and int(hdr['intent_code']) == 1007
+    check(warp, want_sct)
