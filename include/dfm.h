@@ -274,6 +274,25 @@ int dfm_joint_hist(const void *a, const void *b, size_t n, int is_f64, const dou
 int dfm_axis_sums(const void *im, int X, int Y, int Z, int is_f64, double *xs, double *ys, double *zs, void *stream);
 int dfm_overlap_sums(const void *fx, const void *m, size_t n, int is_f64, double *out5, double *work, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Intensity model of ne.models.labels_to_image [UR] (train_synthmorph.py:258-289) -- what
+ * follows the label-map deformation (dfm_vecint_fwd -> dfm_resize_fwd -> dfm_warp_fwd nearest, fill 0).
+ *   dfm_synth_intensity  out[i] = means[l] + stds[l] * N(0,1), l = (int)labels[i] clamped to the table; Philox-4x32-10
+ *                        keyed by `seed`, a pure function of (seed, i).  labels: float label map of n voxels.
+ *   dfm_conv1d_axis      one pass of a separable blur: K (odd) taps along axis 0 / 1 / 2 of [B][X][Y][Z], zero padding.
+ *   dfm_scale_exp_clip   out = clip(img * exp(logbias), lo, hi)   (logbias nullable: clip only).
+ *   dfm_norm_gamma       out = ((img - min_b) / (max_b - min_b)) ** gamma_b per item; minmax: B device {min, max}
+ *                        pairs (float64, from dfm_minmax), gamma: B floats (nullable: 1).
+ *   dfm_onehot           out[i][c] = (lut[(int)labels[i]] == c), channels-last [n][C]; labels outside the table or
+ *                        mapped to a negative entry give an all-zero voxel (out_label_list semantics).
+ * ------------------------------------------------------------------------------------- */
+int dfm_synth_intensity(const float *labels, const float *means, const float *stds, int nlabels, uint64_t seed, float *out,
+                        size_t n, void *stream);
+int dfm_conv1d_axis(const float *in, float *out, int B, int X, int Y, int Z, int axis, const float *taps, int K, void *stream);
+int dfm_scale_exp_clip(const float *img, const float *logbias, float *out, size_t n, float lo, float hi, void *stream);
+int dfm_norm_gamma(const float *img, const double *minmax, const float *gamma, float *out, int B, size_t n_per_item, void *stream);
+int dfm_onehot(const float *labels, const int *lut, int nlut, int C, float *out, size_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

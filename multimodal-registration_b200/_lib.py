@@ -49,6 +49,11 @@ SIGNATURES = {
     'dfm_joint_hist': (_i, [_p, _p, _z, _i, _p, _p, _i, _p, _p]),
     'dfm_axis_sums': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     'dfm_overlap_sums': (_i, [_p, _p, _z, _i, _p, _p, _p]),
+    'dfm_synth_intensity': (_i, [_p, _p, _p, _i, _u64, _p, _z, _p]),
+    'dfm_conv1d_axis': (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
+    'dfm_scale_exp_clip': (_i, [_p, _p, _p, _z, _f, _f, _p]),
+    'dfm_norm_gamma': (_i, [_p, _p, _p, _p, _i, _z, _p]),
+    'dfm_onehot': (_i, [_p, _p, _i, _i, _p, _z, _p]),
     'dfm_cl_to_planar': (_i, [_p, _p, _i, _i, _z, _i, _p]),
     'dfm_planar_to_cl': (_i, [_p, _p, _i, _i, _z, _i, _p]),
 }

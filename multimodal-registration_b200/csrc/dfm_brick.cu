@@ -753,18 +753,10 @@ int launch_ss_brick(const float *src, const float *own, float *out, int B, int X
     if (src != own) bound = nullptr;                  // the bound describes `own`, the box is cut from `src`
     // x/y extent = 8 (tile) + 1 (upper corner) + 1 (straddle) + deformation slack;
     // z pitch 64 = 32 + 1 + 1 + 3 (origin alignment) + slack, and bank-conflict free
-    static const int cfg = getenv("DFM_BRICK_CFG") ? atoi(getenv("DFM_BRICK_CFG")) : 0;     // tuning aid
 #define DFM_SS(TXv, SX, SY, SZ, LX, LY, LZ)                                                                  \
     return large_box ? launch_ss_brick_t<TXv, LX, LY, LZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, bound, bscale, st) \
                      : launch_ss_brick_t<TXv, SX, SY, SZ>(src, own, out, B, Xs, Ys, Zs, X, Y, Z, scale, bound, bscale, st)
-    switch (cfg) {
-        case 1: DFM_SS(4, 6, 10, 40, 8, 12, 48);
-        case 2: DFM_SS(4, 6, 10, 64, 8, 12, 64);
-        case 3: DFM_SS(8, 10, 10, 40, 12, 12, 48);
-        case 4: DFM_SS(8, 10, 10, 64, 12, 12, 64);
-        case 5: DFM_SS(2, 4, 10, 40, 6, 12, 48);
-        default: DFM_SS(4, 6, 12, 40, 8, 12, 48);
-    }
+    DFM_SS(4, 6, 12, 40, 8, 12, 48);     // measured best of six tile / box shapes (round 1, profiles/README.md)
 #undef DFM_SS
 }
 
@@ -888,12 +880,7 @@ int launch_rescale_warp(const float *img, const float *half, float *out, const f
                         const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
                         float pre, int has_fill, float fill, cudaStream_t st) {
     if (!tma_source_ok(img, Xi, Yi, Zi) || Xh < 2 || Yh < 2 || Zh < 2) return DFM_EUNSUPPORTED;
-    static const int cfg = getenv("DFM_FUSED_CFG") ? atoi(getenv("DFM_FUSED_CFG")) : 0;     // tuning aid
-    switch (cfg) {
-        case 1: return launch_rescale_warp_t<4, 8, 14, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
-        case 2: return launch_rescale_warp_t<4, 8, 12, 40>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
-        default: return launch_rescale_warp_t<4, 10, 16, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
-    }
+    return launch_rescale_warp_t<4, 10, 16, 48>(img, half, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, pre, has_fill, fill, st);
 }
 
 static int launch_warp_brick_var(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X,
@@ -940,17 +927,9 @@ int launch_warp_brick(const float *img, const float *field, float *out, int B, i
     static const bool direct = getenv("DFM_WARP_DIRECT") != nullptr;   // tuning aid
     if (direct || (flags & DFM_LOC_ABSOLUTE)) return DFM_EUNSUPPORTED;
     if (!tma_source_ok(img, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
-    static const int cfg = getenv("DFM_WARP_CFG") ? atoi(getenv("DFM_WARP_CFG")) : 0;
-    switch (cfg) {
-        case 0: return launch_warp_brick_var(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 1: return launch_warp_brick_t<4, 10, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 2: return launch_warp_brick_t<8, 16, 16, 64>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 3: return launch_warp_brick_t<4, 10, 18, 72>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 4: return launch_warp_brick_t<8, 14, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 5: return launch_warp_brick_t<4, 8, 12, 40>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        case 6: return launch_warp_brick_t<4, 8, 14, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
-        default: return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);    // round-1 kernel (cfg 20)
-    }
+    static const bool fixed_box = getenv("DFM_WARP_FIXED_BOX") != nullptr;      // tuning aid: the round-1 fixed-box kernel
+    if (fixed_box) return launch_warp_brick_t<4, 10, 16, 48>(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+    return launch_warp_brick_var(img, field, out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
 }
 
 }  // namespace dfm
