@@ -344,7 +344,9 @@ def run_own(args):
                     'pageable_note': 'rank 0 alone, plain (pageable) numpy arrays in, fresh numpy arrays out (copy=True): adds a host '
                                      'memcpy into / out of the pinned staging buffers',
                     'api': 'voxelmorph.networks.VxmDense(...).predict_deform([source, flow]) on pinned host arrays'},
-            'gpu_launches': args.steps * (INT_STEPS + 2),
+            # per step: 7 SS steps (the last two launch a halo-2 and a halo-3 variant of k_ss_march, each batch item runs
+            # in one of them) + k_upsample3_march + k_warp_brick_var = 11 kernels (profiles/r2_launches_bench_b32.csv)
+            'gpu_launches': args.steps * (INT_STEPS + 2 + 2),
             'roofline': {'bound': 'hbm', 'kernel': dom_name, 'achieved': dom['achieved_gbs'], 'peak': peak,
                          'unit': 'GB/s', 'frac': dom['frac_of_peak'],
                          'traffic': TRAFFIC_NCU_B32_GB.get(dom_name) if B == 32 else None,
