@@ -181,6 +181,16 @@ int dfm_resize_bwd(const float *gout, float *gin,
                    const int *zlo, const int *zcnt, const float *zw, int kz,
                    int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
                    float pre, float post, void *stream);
+/* The same with a caller-provided workspace of dfm_resize_bwd_workspace_bytes(B, C, Xi, Yi, Zo) bytes: up-sampling
+ * adjoints (>= 3 taps per axis) then run as two separable passes (x,y then z: K^2 + K instead of K^3 gathers per input
+ * sample).  work == NULL is dfm_resize_bwd. */
+size_t dfm_resize_bwd_workspace_bytes(int B, int C, int Xi, int Yi, int Zo);
+int dfm_resize_bwd_ws(const float *gout, float *gin, float *work,
+                      const int *xlo, const int *xcnt, const float *xw, int kx,
+                      const int *ylo, const int *ycnt, const float *yw, int ky,
+                      const int *zlo, const int *zcnt, const float *zw, int kz,
+                      int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
+                      float pre, float post, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Jacobian-determinant map  (eval_reg_with_jacobian.py:62-78)

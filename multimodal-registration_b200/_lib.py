@@ -34,6 +34,8 @@ SIGNATURES = {
     'dfm_ss_step_bwd_bounded': (_i, [_p] * 4 + [_f] + [_i] * 4 + [_f, _p]),
     'dfm_resize_fwd': (_i, [_p] * 5 + [_i] * 8 + [_f, _f, _i, _u, _p]),
     'dfm_resize_bwd': (_i, [_p, _p] + [_p, _p, _p, _i] * 3 + [_i] * 8 + [_f, _f, _p]),
+    'dfm_resize_bwd_workspace_bytes': (_z, [_i] * 5),
+    'dfm_resize_bwd_ws': (_i, [_p, _p, _p] + [_p, _p, _p, _i] * 3 + [_i] * 8 + [_f, _f, _p]),
     'dfm_jacdet_workspace_bytes': (_z, [_i] * 4),
     'dfm_jacdet': (_i, [_p] * 4 + [_i] * 6 + [_u, _p]),
     'dfm_stitch_subvol': (_i, [_p, _p, _p] + [_i] * 8 + [_u, _p]),

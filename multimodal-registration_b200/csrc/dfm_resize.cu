@@ -488,6 +488,73 @@ k_resize_bwd(const float *__restrict__ gout, float *__restrict__ gin, const int 
     }
 }
 
+// Two-pass separable form of the same adjoint for up-sampling factors (K >= 3 taps per axis): the K^3 gathers per coarse
+// voxel of k_resize_bwd become K^2 + K.  Pass 1 reduces x and y at full z resolution (thread = (iy, z_fine) of one
+// coarse x plane; every load is a coalesced row segment, the K^2 rows of neighbouring threads overlap in L1), pass 2
+// reduces z.  Traffic: N_out read + N_out/4 written and read back + N_in written (x2 zoom), against N_out * K^3 / 8
+// sector-granular gathers before.  Same weights, a different summation order than the one-pass kernel.
+// block = 32 fine z x 8 coarse y; a thread walks RXS consecutive coarse x: the K rows of neighbouring iy and the K planes
+// of consecutive ix overlap, and both overlaps are served by L1 (the first version, one (iy, z) row per block, re-read every
+// fine element 6 times from L2 and ran at the one-pass kernel's speed)
+constexpr int RXS = 4;
+template <int K>
+__global__ void __launch_bounds__(256)
+k_resize_bwd_xy(const float *__restrict__ gout, float *__restrict__ mid, const int *__restrict__ xlo, const float *__restrict__ xw,
+                int kx, const int *__restrict__ ylo, const float *__restrict__ yw, int ky, int Xi, int Yi, int Xo, int Yo, int Zo,
+                int nxt) {
+    const uint32_t z = blockIdx.x * 32u + (threadIdx.x & 31u), iy = blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (z >= (uint32_t)Zo || iy >= (uint32_t)Yi) return;
+    const uint32_t bc = blockIdx.z / (uint32_t)nxt, ix0 = (blockIdx.z - bc * (uint32_t)nxt) * RXS;
+    const float *gb = gout + (size_t)bc * Xo * Yo * Zo + z;
+    const int y0 = __ldg(ylo + iy);
+    float wy[K];
+    uint32_t oy[K];
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+        wy[b] = b < ky ? __ldg(yw + iy * ky + b) : 0.f;
+        oy[b] = (uint32_t)min(y0 + b, Yo - 1) * (uint32_t)Zo;
+    }
+    // (sharing each plane's y reduction between the outputs of the walk through a run-time plane loop was measured
+    // slower -- 950 vs 733 us at B = 16: the loop serialises the loads that full unrolling keeps in flight together)
+#pragma unroll
+    for (int r = 0; r < RXS; ++r) {
+        const uint32_t ix = ix0 + r;
+        if (ix >= (uint32_t)Xi) break;
+        const int x0 = __ldg(xlo + ix);
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            const float wx = a < kx ? __ldg(xw + ix * kx + a) : 0.f;
+            const float *pl = gb + (size_t)min(x0 + a, Xo - 1) * Yo * Zo;
+            float accy = 0.f;
+#pragma unroll
+            for (int b = 0; b < K; ++b) accy = fmaf(wy[b], __ldg(pl + oy[b]), accy);
+            acc = fmaf(wx, accy, acc);
+        }
+        mid[(size_t)bc * Xi * Yi * Zo + ((size_t)ix * Yi + iy) * Zo + z] = acc;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_resize_bwd_z(const float *__restrict__ mid, float *__restrict__ gin, const int *__restrict__ zlo, const float *__restrict__ zw, int kz,
+               int Zi, int Zo, float s, FastDiv zdiv, size_t rows) {
+    // thread = one coarse sample of one row; consecutive threads read overlapping K-wide windows of the same fine row
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= rows * (size_t)Zi) return;
+    const uint32_t row = (uint32_t)(e / (uint32_t)Zi), iz = (uint32_t)(e - (size_t)row * Zi);
+    (void)zdiv;
+    const float *src = mid + (size_t)row * Zo;
+    const int z0 = __ldg(zlo + iz);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const float w = c < kz ? __ldg(zw + iz * kz + c) : 0.f;
+        acc = fmaf(w, __ldg(src + min(z0 + c, Zo - 1)), acc);
+    }
+    gin[e] = s * acc;
+}
+
 }  // namespace dfm
 
 using namespace dfm;
@@ -519,10 +586,23 @@ extern "C" int dfm_resize_fwd(const float *in, float *out, const float *cx, cons
     return launch_resize<DFM_NEAREST>(in, out, cx, cy, cz, B, C, Xi, Yi, Zi, Xo, Yo, Zo, pre, post, flags, st);
 }
 
+extern "C" size_t dfm_resize_bwd_workspace_bytes(int B, int C, int Xi, int Yi, int Zo) {
+    if (B <= 0 || C <= 0 || Xi <= 0 || Yi <= 0 || Zo <= 0) return 0;
+    return (size_t)B * C * Xi * Yi * Zo * sizeof(float);
+}
+
 extern "C" int dfm_resize_bwd(const float *gout, float *gin, const int *xlo, const int *xcnt, const float *xw, int kx,
                               const int *ylo, const int *ycnt, const float *yw, int ky, const int *zlo, const int *zcnt,
                               const float *zw, int kz, int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo, int Zo,
                               float pre, float post, void *stream) {
+    return dfm_resize_bwd_ws(gout, gin, nullptr, xlo, xcnt, xw, kx, ylo, ycnt, yw, ky, zlo, zcnt, zw, kz, B, C, Xi, Yi, Zi, Xo, Yo,
+                             Zo, pre, post, stream);
+}
+
+extern "C" int dfm_resize_bwd_ws(const float *gout, float *gin, float *work, const int *xlo, const int *xcnt, const float *xw,
+                                 int kx, const int *ylo, const int *ycnt, const float *yw, int ky, const int *zlo,
+                                 const int *zcnt, const float *zw, int kz, int B, int C, int Xi, int Yi, int Zi, int Xo, int Yo,
+                                 int Zo, float pre, float post, void *stream) {
     DFM_REQUIRE(B >= 0 && C >= 1 && Xi >= 1 && Yi >= 1 && Zi >= 1 && Xo >= 0 && Yo >= 0 && Zo >= 0, DFM_EINVAL,
                 "dfm_resize_bwd: bad shape");
     DFM_REQUIRE(kx >= 1 && ky >= 1 && kz >= 1, DFM_EINVAL, "dfm_resize_bwd: tap counts must be >= 1");
@@ -539,6 +619,24 @@ extern "C" int dfm_resize_bwd(const float *gout, float *gin, const int *xlo, con
     cudaStream_t st = (cudaStream_t)stream;
     const FastDiv fd = make_fastdiv(Zi);
     const float sc = pre * post;
+    static const bool one_pass = getenv("DFM_RESIZE_BWD_ONEPASS") != nullptr;      // tuning / testing aid
+    if (work && K >= 3 && !one_pass && (uint64_t)B * C * ((Xi + RXS - 1) / RXS) <= 65535) {      // separable two-pass adjoint
+        const size_t rows = (size_t)B * C * Xi * Yi;
+        const int nxt = (Xi + RXS - 1) / RXS;
+        dim3 g1((Zo + 31) / 32, (Yi + 7) / 8, B * C * nxt);
+        const unsigned g2 = (unsigned)((rows * Zi + 255) / 256);
+#define DFM_SEP(KK)                                                                                                         \
+    case KK:                                                                                                                \
+        k_resize_bwd_xy<KK><<<g1, 256, 0, st>>>(gout, work, xlo, xw, kx, ylo, yw, ky, Xi, Yi, Xo, Yo, Zo, nxt);               \
+        k_resize_bwd_z<KK><<<g2, 256, 0, st>>>(work, gin, zlo, zw, kz, Zi, Zo, sc, fd, rows);                               \
+        break;
+        switch (K) {
+            DFM_SEP(3) DFM_SEP(4) DFM_SEP(5) DFM_SEP(6) DFM_SEP(7) DFM_SEP(8)
+            default: return fail(DFM_EUNSUPPORTED, "dfm_resize_bwd: %d taps per input sample (max 8: zoom factors up to ~4)", K);
+        }
+#undef DFM_SEP
+        return check_launch("dfm_resize_bwd(separable)");
+    }
 #define DFM_GO(KK, RX)                                                                                              \
     do {                                                                                                            \
         dim3 grid((plane + 255) / 256, (Xi + RX - 1) / RX, B * C), block(256);                                      \

@@ -402,7 +402,11 @@ class _ResizeLinear(torch.autograd.Function):
         tx, ty, tz = (_coords.device_adjoint_taps(Xi, Xo, dev), _coords.device_adjoint_taps(Yi, Yo, dev),
                       _coords.device_adjoint_taps(Zi, Zo, dev))
         gin = empty(ctx.in_shape, 'planar', gout.device)
-        _lib.call('dfm_resize_bwd', _ptr(gout), _ptr(gin),
+        work = None
+        if max(tx[3], ty[3], tz[3]) >= 3:               # up-sampling adjoint: two separable passes through a workspace
+            work = torch.empty(max(_lib.load().dfm_resize_bwd_workspace_bytes(B, C, Xi, Yi, Zo) // 4, 1), device=gout.device,
+                               dtype=torch.float32)
+        _lib.call('dfm_resize_bwd_ws', _ptr(gout), _ptr(gin), _ptr(work),
                   _ptr(tx[0]), _ptr(tx[1]), _ptr(tx[2]), tx[3], _ptr(ty[0]), _ptr(ty[1]), _ptr(ty[2]), ty[3],
                   _ptr(tz[0]), _ptr(tz[1]), _ptr(tz[2]), tz[3],
                   B, C, Xi, Yi, Zi, Xo, Yo, Zo, float(ctx.pre), float(ctx.post), _stream())

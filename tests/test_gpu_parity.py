@@ -571,6 +571,30 @@ def test_rescale_backward_and_adjointness(factor):
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
 
 
+@pytest.mark.parametrize('shape,factor', [((20, 12, 24), 2), ((7, 9, 33), 2), ((10, 6, 8), 3), ((16, 16, 16), 1.5)])
+def test_rescale_backward_separable_equals_one_pass(shape, factor):
+    """dfm_resize_bwd_ws with a workspace (two separable passes: x,y then z) against dfm_resize_bwd (one pass, K^3 gathers)."""
+    from multimodal_registration_b200 import _coords
+    from multimodal_registration_b200.ops import _ptr, _stream
+    rng = np.random.default_rng(5)
+    B, C = 2, 3
+    Xi, Yi, Zi = shape
+    Xo, Yo, Zo = (int(d * factor) for d in shape)
+    gout = dev(rng.standard_normal((B, Xo, Yo, Zo, C)).astype(np.float32), 'planar')
+    t = [_coords.device_adjoint_taps(a, b, 0) for a, b in ((Xi, Xo), (Yi, Yo), (Zi, Zo))]
+    assert max(tt[3] for tt in t) >= 3
+    outs = []
+    for ws in (False, True):
+        gin = ops.empty((B, Xi, Yi, Zi, C), 'planar', gout.device)
+        gin.fill_(float('nan'))
+        work = torch.empty(mrb._lib.load().dfm_resize_bwd_workspace_bytes(B, C, Xi, Yi, Zo) // 4, device='cuda') if ws else None
+        mrb._lib.call('dfm_resize_bwd_ws', _ptr(gout), _ptr(gin), _ptr(work),
+                      _ptr(t[0][0]), _ptr(t[0][1]), _ptr(t[0][2]), t[0][3], _ptr(t[1][0]), _ptr(t[1][1]), _ptr(t[1][2]), t[1][3],
+                      _ptr(t[2][0]), _ptr(t[2][1]), _ptr(t[2][2]), t[2][3], B, C, Xi, Yi, Zi, Xo, Yo, Zo, float(factor), 1.0, _stream())
+        outs.append(host(gin))
+    np.testing.assert_allclose(outs[1], outs[0], rtol=2e-5, atol=2e-5)
+
+
 def test_compose_backward():
     rng = np.random.default_rng(53)
     a = smooth_noise(rng, (1, 6, 8, 10, 3), 2.0).astype(np.float64)
