@@ -541,19 +541,25 @@ class Graphed:
 # ---------------------------------------------------------------------------------------
 # Jacobian determinant
 # ---------------------------------------------------------------------------------------
-def jacobian_determinant(field, out_dtype=torch.float64, want_det=True, want_stats=True):
+def jacobian_determinant(field, out_dtype=torch.float64, want_det=True, want_stats=True, exact=False):
     """det(I + grad u) on the interior [2:-2]^3 with 4th-order central differences, and the
     statistics of eval_reg_with_jacobian.py:62-91.
 
     field: [B, X, Y, Z, 3] (fp32 or fp64, either physical layout).
     Returns (det [B, X-4, Y-4, Z-4] or None, stats [B, 4] float64 = n_negative, sum, sum of
-    squares, n_total; or None)."""
+    squares, n_total; or None).
+    Planar fp32 fields take the plane-marching kernel, whose stencils and 2x2 minors are fp32 (|error| < 1e-5): a
+    determinant within that distance of zero can land on the other side of it than in the reference's all-float64
+    evaluation.  ``exact=True`` evaluates in float64 like the reference whatever the layout (the fold count then
+    matches ``np.linalg.det`` on the same values; ~8x slower)."""
     _require_cuda(field, 'field')
     if field.dim() != 5 or field.shape[-1] != 3:
         raise ValueError('field must be [B, X, Y, Z, 3], got %s' % (tuple(field.shape),))
     if field.dtype not in (torch.float32, torch.float64):
         field = field.float()
     B, X, Y, Z, _ = field.shape
+    if exact and field.dtype == torch.float32:
+        field = field.double()                              # the all-float64 kernel (eval_reg_with_jacobian.py:51: get_fdata())
     field, f_cl = _field_layout(field, 'field')
     det = torch.empty((B, X - 4, Y - 4, Z - 4), device=field.device, dtype=out_dtype) if want_det else None
     stats = part = None

@@ -595,6 +595,16 @@ def test_rescale_backward_separable_equals_one_pass(shape, factor):
     np.testing.assert_allclose(outs[1], outs[0], rtol=2e-5, atol=2e-5)
 
 
+def test_jacobian_exact_switch_matches_float64_reference():
+    """ops.jacobian_determinant(exact=True): a planar fp32 field evaluated in float64 like the reference lines."""
+    rng = np.random.default_rng(8)
+    f = smooth_noise(rng, (1, 14, 12, 16, 3), 1.5, smooth=1)
+    det, stats = ops.jacobian_determinant(dev(f, 'planar'), exact=True)
+    d, n = jo.jacobian_determinant(f[0][:, :, :, None, :].astype(np.float64))
+    np.testing.assert_allclose(det.cpu().numpy().reshape(-1), d, rtol=0, atol=1e-12)
+    assert int(stats[0, 0]) == n
+
+
 def test_compose_backward():
     rng = np.random.default_rng(53)
     a = smooth_noise(rng, (1, 6, 8, 10, 3), 2.0).astype(np.float64)
