@@ -240,6 +240,23 @@ def test_vecint_marching_kernel(shape, nsteps, std):
     check(host(ops.vecint(s, nsteps).detach()))
 
 
+@pytest.mark.parametrize('shape', [(10, 12, 36), (21, 19, 96), (6, 13, 128), (3, 2, 40)])
+@pytest.mark.parametrize('std', [0.5, 8.0, 60.0])
+def test_compose_shapes_and_displacements(shape, std):
+    """vxm.utils.compose at the shapes the marching SS kernel covers (compose itself runs the bounding-box brick kernel:
+    a marching variant with the displacements read from the second field was measured 2x slower on full-size displacements),
+    small / large / far-out-of-volume displacements, both layouts."""
+    rng = np.random.default_rng(hash(shape) % 2 ** 31)
+    a = smooth(rng, (2,) + shape + (3,), std)
+    b = smooth(rng, (2,) + shape + (3,), std * 0.5)
+    want = np.stack([io.compose([a[i], b[i]]) for i in range(2)])
+    for layout in ('cl', 'planar'):
+        got = host(ops.compose([dev(a, layout), dev(b, layout)]))
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL * max(1.0, std / 8))
+        if mrb._lib.exact_order():
+            np.testing.assert_array_equal(got, want)
+
+
 def test_vecint_marching_nan_and_inf_do_not_hang():
     """NaN / Inf voxels (the reference's int cast of a NaN location is undefined, so there is no oracle for them)
     take the global-gather path without faulting; voxels outside their dependency cone are unaffected."""
