@@ -78,6 +78,11 @@ int launch_rescale_warp(const float *img, const float *half, float *out, const f
                         const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
                         float pre, int has_fill, float fill, cudaStream_t st);
 
+// the same with the image corners fetched by texture gathers and the field marched like the up-sampler -- dfm_warp_tex.cu
+int launch_rescale_warp_tex(const float *img, const float *half, float *out, const float *cx, const float *cy,
+                            const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
+                            float pre, int has_fill, float fill, cudaStream_t st);
+
 // multi-channel planar linear warp through a TMA channel ring -- dfm_brick_mc.cu
 int launch_warp_mc_fwd(const float *img, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi, int X,
                        int Y, int Z, int has_fill, float fill, cudaStream_t st);

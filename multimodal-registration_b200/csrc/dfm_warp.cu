@@ -336,7 +336,9 @@ extern "C" int dfm_rescale_warp_fwd(const float *img, const float *coarse, float
     if (B == 0) return DFM_OK;
     DFM_REQUIRE(img && coarse && out && cx && cy && cz, DFM_EINVAL, "dfm_rescale_warp_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_rescale_warp(img, coarse, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, factor, has_fill, fill, st);
+    int rc = launch_rescale_warp_tex(img, coarse, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, factor, has_fill, fill, st);
+    if (rc != DFM_EUNSUPPORTED) return rc;
+    rc = launch_rescale_warp(img, coarse, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, factor, has_fill, fill, st);
     if (rc != DFM_EUNSUPPORTED) return rc;
     DFM_REQUIRE(work, DFM_EUNSUPPORTED, "dfm_rescale_warp_fwd: fused kernel not applicable to this shape and no work buffer given");
     rc = dfm_resize_fwd(coarse, work, cx, cy, cz, B, 3, Xh, Yh, Zh, X, Y, Z, factor, 1.f, DFM_LINEAR, 0u, stream);
