@@ -43,17 +43,17 @@ def two_steps_tail(moving, fixed, model1, model2, flow1, flow2, warp_interp='lin
     fixed = _host.to_device(fixed, torch.float32, tag='fixed')
     inshape = model1.inshape
     if warp_interp == 'linear':
-        moved_first, warp_first = model1.deform([moving, _host.to_device(flow1, torch.float32, tag='flow1')])        # :318-319
-        moved, warp_second = model2.deform([moved_first, _as_flow(flow2, moved_first, fixed)])                         # :320-321
+        moved_first, warp_first = model1.deform([moving, _host.to_device(flow1, torch.float32, tag='flow1')], keep_pos_flow=False)   # :318-319
+        moved, warp_second = model2.deform([moved_first, _as_flow(flow2, moved_first, fixed)], keep_pos_flow=False)     # :320-321
         scale = _scale_of(warp_first, inshape)
         warp = ops.compose([warp_first, warp_second])                                                                  # :324
     else:
-        _, warp_first = model1.deform([moving, _host.to_device(flow1, torch.float32, tag='flow1')])                    # :328-329
+        _, warp_first = model1.deform([moving, _host.to_device(flow1, torch.float32, tag='flow1')], keep_pos_flow=False)   # :328-329
         scale = _scale_of(warp_first, inshape)
         src = moving if moving_proc is None else _host.to_device(moving_proc, torch.float32, tag='moving_proc')
         tr = networks.Transform(src.shape[1:-1], interp_method=warp_interp, rescale=scale, nb_feats=src.shape[-1])
         moved_first = tr([src, warp_first])                                                                            # :338-341
-        _, warp_second = model2.deform([moved_first, _as_flow(flow2, moved_first, fixed)])                             # :343-344
+        _, warp_second = model2.deform([moved_first, _as_flow(flow2, moved_first, fixed)], keep_pos_flow=False)       # :343-344
         warp = ops.compose([warp_first, warp_second])                                                                  # :346
         moved = tr([src, warp])                                                                                        # :354-355
     return dict(moved=moved, warp=warp, scale=scale, moved_first_reg=moved_first, warp_first_reg=warp_first,
@@ -82,8 +82,8 @@ def two_steps_tail_subvol(moving, lst_subvol_mov, lst_subvol_fx, lst_coords_subv
     for k, (mov, fx) in enumerate(zip(lst_subvol_mov, lst_subvol_fx)):
         mov = _host.to_device(mov, torch.float32, tag='subvol_mov')
         fx = _host.to_device(fx, torch.float32, tag='subvol_fx')
-        moved_first, w1 = model1.deform([mov, _host.to_device(flows1[k], torch.float32, tag='flow1')])               # :361-362
-        _, w2 = model2.deform([moved_first, _as_flow(flows2[k], moved_first, fx)])                                     # :363-364
+        moved_first, w1 = model1.deform([mov, _host.to_device(flows1[k], torch.float32, tag='flow1')], keep_pos_flow=False)   # :361-362
+        _, w2 = model2.deform([moved_first, _as_flow(flows2[k], moved_first, fx)], keep_pos_flow=False)               # :363-364
         fields.append(ops.to_layout(ops.compose([w1, w2]), 'cl')[0])                                                   # :365-367
     half = int(fields[0].shape[0]) != int(model1.inshape[0])                                                          # :369
     scale = 2 if half else 1

@@ -394,6 +394,42 @@ def test_fused_rescale_warp_matches_unfused_bitwise():
             assert_linear_parity(fused, io.spatial_transformer(scan, io.rescale_dense_transform(half, 2), 'linear', fv))
 
 
+def test_fused_texture_gather_path():
+    """dfm_rescale_warp_fwd on shapes its texture-gather kernel covers (dfm_warp_tex.cu): same arithmetic as the marching
+    up-sampler followed by the warp, so it must equal the two stand-alone kernels BIT FOR BIT in both builds, and the
+    oracle within the bar.  Cases: more than one launch's worth of texture objects (B > 32), ragged tiles (Y, Z not
+    multiples of 16 / 32), a non-integer zoom, an image larger than the field grid, fill values."""
+    rng = np.random.default_rng(611)
+    cases = [((8, 12, 16), 33, 2, None, None), ((9, 11, 20), 1, 2, 0.0, None), ((8, 12, 16), 1, 1.5, None, None),
+             ((8, 12, 16), 2, 2, -1.0, (20, 24, 32)), ((20, 24, 40), 3, 2, None, None)]
+    for shape, B, factor, fv, img_shape in cases:
+        full = tuple(int(s * factor) for s in shape)
+        half = smooth_noise(rng, (B,) + shape + (3,), 2.5, smooth=1)
+        scan = rng.random((B,) + (img_shape or full) + (1,)).astype(np.float32)
+        d_scan, d_half = dev(scan), dev(half, 'planar')
+        fused = host(ops.rescale_warp(d_scan, d_half, factor, fv))
+        flow = ops.rescale_dense_transform(d_half, factor)
+        unfused = host(ops.warp(d_scan, flow, 'linear', fv))
+        np.testing.assert_array_equal(fused, unfused)
+        if B <= 3:
+            want = io.spatial_transformer(scan, io.rescale_dense_transform(half, factor), 'linear', fv)
+            if fv is None or mrb._lib.exact_order():
+                assert_linear_parity(fused, want)
+            else:                                                   # a few-ulp flow change can flip a voxel across the fill boundary
+                assert np.mean(~np.isclose(fused, want, rtol=RTOL, atol=ATOL)) < 1e-3
+
+
+def test_fused_texture_gather_is_reproducible():
+    """The coarse-plane ring of the fused kernel is released by data-dependent arrivals (a consumer's arrival must not
+    overtake its shared loads): many launches at a size with thousands of CTAs give the same bits every time."""
+    rng = np.random.default_rng(612)
+    half = dev(smooth_noise(rng, (4, 40, 40, 48, 3), 3.0, smooth=1), 'planar')
+    scan = dev(rng.random((4, 80, 80, 96, 1)).astype(np.float32))
+    ref = ops.warp(scan, ops.rescale_dense_transform(half, 2))
+    for _ in range(25):
+        assert torch.equal(ops.rescale_warp(scan, half, 2), ref)
+
+
 # --------------------------------------------------------------------------------------
 # Jacobian determinant
 # --------------------------------------------------------------------------------------
