@@ -43,6 +43,20 @@ __device__ __forceinline__ void wt_arrive_after(uint64_t *bar, uint32_t dep, uin
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
+// One axis of the sampling set-up with the corner index kept in FLOAT (it only feeds texture coordinates): the same
+// values as axis_fast -- cl = clip(loc), i1 = min(trunc(cl) + 1, max), w_lo = i1 - cl -- without the float -> int -> float
+// round trip.  trunc(cl) for 0 <= cl < 2^22 is (cl +rz 2^23) - 2^23, both steps exact.
+struct AxisT {
+    float i1, w0;
+};
+__device__ __forceinline__ AxisT axis_tex(float loc, float maxf) {
+    const float cl = fminf(fmaxf(loc, 0.f), maxf);
+    AxisT a;
+    a.i1 = fminf(__fadd_rn(__fsub_rn(__fadd_rz(cl, 8388608.f), 8388608.f), 1.f), maxf);
+    a.w0 = __fsub_rn(a.i1, cl);
+    return a;
+}
+
 // a voxel pair between issuing its four tld4 and consuming them
 struct TexPend {
     float4 loA, hiA, loB, hiB;
@@ -88,7 +102,8 @@ __device__ __forceinline__ void exact_field(const float (&V)[2][3][2][3], const 
 
 // 72 registers -> 3 CTAs (24 consumer warps) per SM.  Measured at B=32 (160x160x192): 0.727 ms; a software-pipelined variant
 // (the gathers of plane x+1 issued before the results of plane x are consumed: 96 registers, 2 CTAs/SM) 0.93 ms, 4 CTAs/SM at
-// 56 registers 0.728 ms -- resident warps, not gathers in flight per thread, hide the texture latency.
+// 56 registers 0.728 ms -- resident warps, not gathers in flight per thread, hide the texture latency.  A hybrid that
+// fetched the upper x plane's four corners with LDG (L1 hits) to relieve the texture write-back: 0.85 ms (slower).
 template <bool HF>
 __global__ void __launch_bounds__((W_NCW + 1) * 32, 3)
 k_rescale_warp_tex(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TexSet texs, float *__restrict__ out,
@@ -142,8 +157,7 @@ k_rescale_warp_tex(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     const int off0 = (ayA.i1 - 1 - by0) * WBZ + (az.i1 - 1 - bz0);
     float *pA = out + (size_t)(b0 + blockIdx.z) * No + ((size_t)jx0 * Yo + min(jyA, Yo - 1)) * Zo + min(jz, Zo - 1);
     // image side
-    const int mxi = Xi - 1, myi = Yi - 1, mzi = Zi - 1;
-    const float mxf = (float)mxi, myf = (float)myi, mzf = (float)mzi;
+    const float mxf = (float)(Xi - 1), myf = (float)(Yi - 1), mzf = (float)(Zi - 1);
     const float fyA = (float)min(jyA, Yo - 1), fyB = (float)min(jyA + 1, Yo - 1), fz = (float)min(jz, Zo - 1);
     const float rowstep = (float)Yi;
     float fx = (float)jx0;
@@ -157,11 +171,12 @@ k_rescale_warp_tex(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             if (lxA < 0.f || lxA > mxf || lyA < 0.f || lyA > myf || lzA < 0.f || lzA > mzf) q.oob |= 1u;
             if (lxB < 0.f || lxB > mxf || lyB < 0.f || lyB > myf || lzB < 0.f || lzB > mzf) q.oob |= 2u;
         }
-        const AxisF axA = axis_fast(lxA, mxf, mxi), ayA2 = axis_fast(lyA, myf, myi), azA = axis_fast(lzA, mzf, mzi);
-        const AxisF axB = axis_fast(lxB, mxf, mxi), ayB2 = axis_fast(lyB, myf, myi), azB = axis_fast(lzB, mzf, mzi);
-        // texels (i1-1, i1) along z and rows (r, r+1), r = (ix1-1)*Yi + iy1-1: footprint centre at (iz1, r+1)
-        const float uA = (float)azA.i1, vA = (float)((axA.i1 - 1) * Yi + ayA2.i1);
-        const float uB = (float)azB.i1, vB = (float)((axB.i1 - 1) * Yi + ayB2.i1);
+        const AxisT axA = axis_tex(lxA, mxf), ayA2 = axis_tex(lyA, myf), azA = axis_tex(lzA, mzf);
+        const AxisT axB = axis_tex(lxB, mxf), ayB2 = axis_tex(lyB, myf), azB = axis_tex(lzB, mzf);
+        // texels (i1-1, i1) along z and rows (r, r+1), r = (ix1-1)*Yi + iy1-1: footprint centre at (iz1, r+1); integers
+        // below 2^24 (host: Xi*Yi <= 65000), so the float arithmetic is exact
+        const float uA = azA.i1, vA = fmaf(axA.i1, rowstep, __fsub_rn(ayA2.i1, rowstep));
+        const float uB = azB.i1, vB = fmaf(axB.i1, rowstep, __fsub_rn(ayB2.i1, rowstep));
         q.loA = tex2Dgather<float4>(tex, uA, vA, 0);
         q.hiA = tex2Dgather<float4>(tex, uA, vA + rowstep, 0);
         q.loB = tex2Dgather<float4>(tex, uB, vB, 0);

@@ -27,7 +27,7 @@ for rep in range(2):
         cur.wait_stream(s_in)
         src_d.record_stream(cur); flow_d.record_stream(cur)
         c0 = torch.cuda.Event(enable_timing=True); c0.record()
-        y, second = model.deform([src_d, flow_d])
+        y, second = model.deform([src_d, flow_d], keep_pos_flow=False)
         y_c = ops.to_layout(y, 'cl')
         c1 = torch.cuda.Event(enable_timing=True); c1.record()
         s_out.wait_stream(cur)

@@ -19,4 +19,4 @@ for _ in range(20):
     ops.rescale_warp(img, half, 2)
 b.record()
 torch.cuda.synchronize()
-print('variant %s carve %s: %.3f ms identical %s' % (os.environ.get('DFM_TEX_VARIANT', '-'), os.environ.get('DFM_TEX_CARVEOUT', '-'), a.elapsed_time(b) / 20, ok))
+print('hyb %s carve %s: %.3f ms identical %s' % (os.environ.get('DFM_TEX_HYB', '-'), os.environ.get('DFM_TEX_CARVEOUT', '-'), a.elapsed_time(b) / 20, ok))

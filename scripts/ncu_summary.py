@@ -9,6 +9,8 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'launch__registers_per_thread', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tex.avg.pct_of_peak_sustained_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'smsp__inst_executed.sum', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',

@@ -13,7 +13,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'multimodal-regis
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 names = {}
 demangled = subprocess.run(['cu++filt'], input='\n'.join(set(re.findall(r'Function : (\S+)', sass))), capture_output=True, text=True)
-KEYS = ['UTMALDG', 'UTMASTG', 'SYNCS', 'LDS', 'STS', 'LDG', 'STG', 'REDG', 'ATOMG', 'ATOMS', 'SHFL', 'FFMA2', 'FMUL2', 'FADD2', 'FFMA', 'MMA']
+KEYS = ['UTMALDG', 'UTMASTG', 'SYNCS', 'TLD4', 'LDS', 'STS', 'LDG', 'STG', 'REDG', 'ATOMG', 'ATOMS', 'SHFL', 'FFMA2', 'FMUL2', 'FADD2', 'FFMA', 'MMA']
 rows = []
 cur, cnt, total = None, None, 0
 for line in sass.splitlines():
