@@ -379,7 +379,7 @@ def run_own(args):
 
 K_SS = 'ss_step(k_ss_march)'
 K_RS = 'rescale_x2(k_upsample3_march)'
-K_WP = 'warp_linear(k_warp_brick_var)'
+K_WP = 'warp_linear(k_warp_tex)'
 K_FU = 'rescale_warp_fused(k_rescale_warp_tex)'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B=32, from the committed `ncu --set full` capture of
 # `python bench.py --steps 2 --warmup 3 --batch 32 --no-e2e` (profiles/r2_b32_ncu_full_summary.csv; the SS entry is
@@ -388,7 +388,7 @@ K_FU = 'rescale_warp_fused(k_rescale_warp_tex)'
 TRAFFIC_NCU_B32_GB = {
     K_SS: 0.25637 + 0.19567,
     K_RS: 0.25414 + 1.82949,
-    K_WP: 2.51661 + 0.61712,
+    K_WP: 2.51435 + 0.61650,
     K_FU: 0.86307 + 0.59855,
 }
 

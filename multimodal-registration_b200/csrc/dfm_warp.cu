@@ -300,8 +300,10 @@ extern "C" int dfm_warp_fwd(const void *img, const float *field, void *out, int 
     cudaStream_t st = (cudaStream_t)stream;
     if (interp == DFM_LINEAR) {
         DFM_REQUIRE(elem_size == 4, DFM_EINVAL, "dfm_warp_fwd: linear interpolation needs fp32 (elem_size 4), got %d", elem_size);
-        if (C == 1) {   // one channel: TMA-brick path (dfm_brick.cu), falls through if not applicable
-            int rc = launch_warp_brick((const float *)img, field, (float *)out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+        if (C == 1) {   // one channel: texture gathers where selected (dfm_warp_tex.cu), else the TMA-brick path (dfm_brick.cu)
+            int rc = launch_warp_tex((const float *)img, field, (float *)out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
+            if (rc != DFM_EUNSUPPORTED) return rc;
+            rc = launch_warp_brick((const float *)img, field, (float *)out, B, Xi, Yi, Zi, X, Y, Z, has_fill, fill, flags, st);
             if (rc != DFM_EUNSUPPORTED) return rc;
         }
         if (C > 1 && (flags & DFM_IMG_CL)) {   // channels-last multi-channel (the reference layout): lanes over channels

@@ -295,6 +295,61 @@ k_rescale_warp_tex(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #endif
 }
 
+// ---------------------------------------------------------------------------------------
+// Stand-alone one-channel linear warp with the same texture gathers: the field streams through registers (planar or
+// channels-last), a thread owns one (y, z) column of NX consecutive x planes (the upper plane of voxel x is the lower plane
+// of voxel x+1: an L1 hit), lane = z.  No brick, no bounding box, no fit rate: the time does not depend on how strongly the
+// field deforms.  Same arithmetic as k_warp_brick_var / launch_linear (bit-identical in both builds).
+// ---------------------------------------------------------------------------------------
+template <bool FIELD_CL, bool HF>
+__global__ void __launch_bounds__(256)
+k_warp_tex(const __grid_constant__ TexSet texs, const float *__restrict__ field, float *__restrict__ out, int Xi, int Yi, int Zi,
+           int X, int Y, int Z, float fill, FastDiv nzt, FastDiv nyzt, int b0) {
+    constexpr int NX = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xt = (int)fast_div(blockIdx.x, nyzt), rem = (int)blockIdx.x - xt * (int)nyzt.d;
+    const int yt = (int)fast_div((uint32_t)rem, nzt), zt = rem - yt * (int)nzt.d;
+    const int z = zt * 32 + lane, y = yt * 8 + warp, x0 = xt * NX;
+    if (z >= Z || y >= Y) return;
+    const cudaTextureObject_t tex = texs.t[blockIdx.y];
+    const uint32_t N = (uint32_t)X * Y * Z, XS = (uint32_t)Y * Z;
+    const size_t b = (size_t)(b0 + blockIdx.y);
+    const float *fb = field + b * 3 * N;
+    float *ob = out + b * N;
+    const uint32_t vox0 = ((uint32_t)x0 * Y + y) * Z + z;
+    const float mxf = (float)(Xi - 1), myf = (float)(Yi - 1), mzf = (float)(Zi - 1);
+    const float fy = (float)y, fz = (float)z, rowstep = (float)Yi;
+    float l[3][NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const uint32_t vox = vox0 + (uint32_t)min(i, X - 1 - x0) * XS;            // shadow the last valid plane
+        if (FIELD_CL) {
+            l[0][i] = __ldg(fb + (size_t)vox * 3); l[1][i] = __ldg(fb + (size_t)vox * 3 + 1); l[2][i] = __ldg(fb + (size_t)vox * 3 + 2);
+        } else {
+            l[0][i] = __ldg(fb + vox); l[1][i] = __ldg(fb + N + vox); l[2][i] = __ldg(fb + 2 * (size_t)N + vox);
+        }
+    }
+    float4 lo[NX], hi[NX];
+    AxisT ax[NX], ay[NX], az[NX];
+    unsigned oob = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        const float lx = __fadd_rn((float)min(x0 + i, X - 1), l[0][i]), ly = __fadd_rn(fy, l[1][i]), lz = __fadd_rn(fz, l[2][i]);
+        if (HF && (lx < 0.f || lx > mxf || ly < 0.f || ly > myf || lz < 0.f || lz > mzf)) oob |= 1u << i;
+        ax[i] = axis_tex(lx, mxf); ay[i] = axis_tex(ly, myf); az[i] = axis_tex(lz, mzf);
+        const float u = az[i].i1, v = fmaf(ax[i].i1, rowstep, __fsub_rn(ay[i].i1, rowstep));
+        lo[i] = tex2Dgather<float4>(tex, u, v, 0);
+        hi[i] = tex2Dgather<float4>(tex, u, v + rowstep, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        if (x0 + i >= X) break;
+        float r = tex_finish(lo[i], hi[i], ax[i].w0, ay[i].w0, az[i].w0);
+        if (HF && (oob & (1u << i))) r = fill;
+        ob[vox0 + i * XS] = r;
+    }
+}
+
 // ------------------------------- host side -----------------------------------------------
 // Texture objects are descriptors over caller memory (no copy).  Creating one costs a few microseconds of host time,
 // so they are cached per (device, base pointer, width, rows); the cache is bounded and evicts the oldest entry.
@@ -438,6 +493,38 @@ int launch_rescale_warp_tex(const float *img, const float *half, float *out, con
         else
             k_rescale_warp_tex<false><<<grid, block, 0, st>>>(tmap, ts, out, cx, cy, cz, Xh, Yh, Zh, X, Y, Z, Xi, Yi, Zi, pre, 1.f, fill, nzt, b0, 0u);
         const int rc = check_launch("k_rescale_warp_tex");
+        if (rc) return rc;
+    }
+    return DFM_OK;
+}
+
+int launch_warp_tex(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X, int Y, int Z,
+                    int has_fill, float fill, unsigned flags, cudaStream_t st) {
+    // measured on B200 (B=32, 160x160x192): 0.788 / 0.726 / 0.707 ms on the bench field x1 / x0.3 / x0 against 0.806 / 0.756 /
+    // 0.751 ms for the TMA-brick kernel, so this is the default where the image can be described as a texture;
+    // DFM_WARP_TEX=0 (read per call: the tests switch it) selects the brick kernel
+    const char *sel = getenv("DFM_WARP_TEX");
+    const bool on = sel == nullptr || atoi(sel) != 0;
+    if (!on || (flags & DFM_LOC_ABSOLUTE) || !tex_volume_ok(img, B, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
+    const int nzt = (Z + 31) / 32, nyt = (Y + 7) / 8, nxt = (X + 1) / 2;
+    if ((unsigned long long)nzt * nyt * nxt * ((unsigned long long)nzt * nyt) >= (1ull << 32)) return DFM_EUNSUPPORTED;   // fast_div range
+    std::vector<cudaTextureObject_t> all((size_t)B);
+    for (int b = 0; b < B; ++b)
+        if (!tex_for_volume(img + (size_t)b * Xi * Yi * Zi, Zi, Xi * Yi, &all[(size_t)b])) return DFM_EUNSUPPORTED;
+    const FastDiv dz = make_fastdiv((uint32_t)nzt), dyz = make_fastdiv((uint32_t)(nzt * nyt));
+    for (int b0 = 0; b0 < B; b0 += W_TEX_PER_LAUNCH) {
+        const int nb = min(W_TEX_PER_LAUNCH, B - b0);
+        TexSet ts = {};
+        for (int i = 0; i < nb; ++i) ts.t[i] = all[(size_t)(b0 + i)];
+        dim3 grid((unsigned)(nzt * nyt * nxt), nb, 1), block(256);
+#define DFM_WT(FC, HFv) k_warp_tex<FC, HFv><<<grid, block, 0, st>>>(ts, field, out, Xi, Yi, Zi, X, Y, Z, fill, dz, dyz, b0)
+        if (flags & DFM_FIELD_IN_CL) {
+            if (has_fill) DFM_WT(true, true); else DFM_WT(true, false);
+        } else {
+            if (has_fill) DFM_WT(false, true); else DFM_WT(false, false);
+        }
+#undef DFM_WT
+        const int rc = check_launch("k_warp_tex");
         if (rc) return rc;
     }
     return DFM_OK;

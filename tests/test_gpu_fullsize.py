@@ -90,7 +90,12 @@ def test_headline_pipeline_at_baseline_shape():
     report('RescaleTransform(2)', host(g_flow_f), flow_f)
     # the warp is checked on the ORACLE's field so that its error is its own
     d_flow_f = dev(flow_f, 'planar')
-    report('linear warp 160x160x192', host(ops.warp(d_img, d_flow_f)), moved)
+    report('linear warp 160x160x192 (texture-gather kernel)', host(ops.warp(d_img, d_flow_f)), moved)
+    os.environ['DFM_WARP_TEX'] = '0'            # the TMA-brick kernel in the regime the round-1 verdict named (bench field)
+    try:
+        report('linear warp 160x160x192 (TMA-brick kernel)', host(ops.warp(d_img, d_flow_f)), moved)
+    finally:
+        del os.environ['DFM_WARP_TEX']
     report('linear warp 160x160x192, channels-last field', host(ops.warp(d_img, dev(flow_f, 'cl'))), moved)
     got_nn = host(ops.warp(dev(labels), d_flow_f, 'nearest', 0))
     np.testing.assert_array_equal(got_nn, moved_nn)           # label warps: bit-exact in both builds

@@ -394,6 +394,43 @@ def test_fused_rescale_warp_matches_unfused_bitwise():
             assert_linear_parity(fused, io.spatial_transformer(scan, io.rescale_dense_transform(half, 2), 'linear', fv))
 
 
+class warp_kernel:
+    """Select the one-channel linear warp kernel for the calls inside: 'tex' (texture gathers, the default where the
+    image qualifies) or 'brick' (TMA bounding-box brick); the library reads DFM_WARP_TEX per call."""
+
+    def __init__(self, which):
+        self.value = '1' if which == 'tex' else '0'
+
+    def __enter__(self):
+        self.old = os.environ.get('DFM_WARP_TEX')
+        os.environ['DFM_WARP_TEX'] = self.value
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            del os.environ['DFM_WARP_TEX']
+        else:
+            os.environ['DFM_WARP_TEX'] = self.old
+
+
+def test_linear_warp_kernels_agree_bitwise():
+    """The texture-gather warp and the TMA-brick warp share weights, corner order and accumulation: same bits, and both
+    inside the bar against the oracle (planar and channels-last fields, fill values, image larger than the grid, B > 32)."""
+    rng = np.random.default_rng(613)
+    cases = [((16, 24, 32), 2, None, None, 'planar'), ((16, 24, 32), 34, None, None, 'cl'), ((18, 22, 40), 1, 0.0, None, 'planar'),
+             ((16, 24, 32), 2, -1.0, (20, 28, 48), 'cl'), ((40, 40, 96), 2, None, None, 'planar')]
+    for shape, B, fv, img_shape, lay in cases:
+        flow = smooth_noise(rng, (B,) + shape + (3,), 3.0, smooth=1)
+        scan = rng.random((B,) + (img_shape or shape) + (1,)).astype(np.float32)
+        d_scan, d_flow = dev(scan), dev(flow, lay)
+        with warp_kernel('tex'):
+            a = host(ops.warp(d_scan, d_flow, 'linear', fv))
+        with warp_kernel('brick'):
+            b = host(ops.warp(d_scan, d_flow, 'linear', fv))
+        np.testing.assert_array_equal(a, b)
+        if B <= 2:
+            assert_linear_parity(a, io.spatial_transformer(scan, flow, 'linear', fv))
+
+
 def test_fused_texture_gather_path():
     """dfm_rescale_warp_fwd on shapes its texture-gather kernel covers (dfm_warp_tex.cu): same arithmetic as the marching
     up-sampler followed by the warp, so it must equal the two stand-alone kernels BIT FOR BIT in both builds, and the
