@@ -11,7 +11,10 @@
  *
  * Conventions
  *   - every data pointer is a DEVICE pointer owned by the caller; the library allocates
- *     nothing and keeps no device state between calls;
+ *     no device memory and keeps no device state between calls.  The only thing it remembers
+ *     is a bounded host-side cache of texture DESCRIPTORS (cudaTextureObject_t over caller
+ *     memory, keyed by device / base pointer / geometry; no copy of the data) used by the
+ *     one-channel linear warps -- a descriptor names an address range, it does not own it;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no hidden
  *     synchronisation, no default-stream use -> capturable in CUDA graphs;
  *   - volumes are fp32 unless stated.  A tensor is either "planar"  [B][C][X][Y][Z]
@@ -89,9 +92,12 @@ int dfm_warp_channelwise_fwd(const float *vol, const float *shift, void *out, in
 /* Fused RescaleTransform(factor >= 1) + linear SpatialTransformer of a one-channel image: the
  * deformation tail of VxmDense at inference (3d_reg.py:305,310; bids_*.py:311-322), where the
  * full-resolution warp is only an intermediate.  out[b,p] = interp(img[b], p + U[b,:,p]) with
- * U = resize(factor * coarse) evaluated on the fly, so U never touches HBM (libdfm_exact.so: same
- * arithmetic as dfm_resize_fwd followed by dfm_warp_fwd, bit for bit; libdfm.so: separable
- * evaluation of the same interpolation, a few ulp from it).
+ * U = resize(factor * coarse) evaluated on the fly, so U never touches HBM.  Where the shapes allow
+ * (up-sampling whose coarse box fits the marching tile, image rows 32-byte multiples, X*Y <= 65000)
+ * the field is marched like dfm_resize_fwd's up-sampler and the image corners are fetched by texture
+ * gathers: the same arithmetic as dfm_resize_fwd followed by dfm_warp_fwd, bit for bit, in both
+ * builds.  Other shapes: libdfm_exact.so the same bits, libdfm.so a separable evaluation a few ulp
+ * from it.
  *   img [B][Xi][Yi][Zi], coarse [B][3][Xh][Yh][Zh] planar, out [B][X][Y][Z]; cx/cy/cz as in
  *   dfm_resize_fwd (X/Y/Z entries).  work: nullable scratch of B*3*X*Y*Z floats used when the
  *   fused kernel is not applicable (then the two kernels run back to back); without it such
