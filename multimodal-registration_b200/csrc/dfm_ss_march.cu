@@ -94,7 +94,9 @@ struct MarchRun {
 
 // TY rows per CTA, VPT of them per thread (rows ty, ty + TY/VPT, ...): the per-step overhead (ring
 // bookkeeping, barrier wait / arrive, loop) is shared by VPT voxels and their gathers interleave.
-template <int TY, int VPT, int H, int R, int NZW, bool IN_CL, bool FIRST>
+// IN_CL: 0 = planar source; 1 = channels-last source in 96-float sub-boxes (any Z); 2 = channels-last source as contiguous rows of
+// 3 Z floats through one 5-D box per plane (Z a multiple of 32): corner addressing with immediate offsets like the planar path
+template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST>
 __global__ void __launch_bounds__((TY / VPT * NZW + 1) * 32, march_ctas(TY, H, R, NZW))
 k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ out, int X,
            int Y, int Z, float scale, int nstrips, unsigned long long total, float *__restrict__ absmax, MarchSel sel) {
@@ -152,7 +154,9 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     if (q >= R) mbar_wait_u(empty_u + 8 * s, ph);
                     mbar_expect_tx(&full[s], (uint32_t)(SLOT * sizeof(float)));
                     float *dst = ring + s * SLOT;
-                    if (IN_CL) {
+                    if (IN_CL == 2) {
+                        tma_load_5d(dst, &tmap, &full[s], 0, 0, r.y0 - H, p, r.b);
+                    } else if (IN_CL == 1) {
 #pragma unroll
                         for (int j = 0; j < NZW; ++j) tma_load_4d(dst + j * (ROWS * 96), &tmap, &full[s], 96 * j, r.y0 - H, p, r.b);
                     } else {
@@ -187,7 +191,8 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
             const int y = r.y0 + tyw + j * TYW, yc = min(y, Y - 1);
             ok[j] = (z < Z) && (y < Y);
             fy[j] = (float)yc;
-            own_off[j] = IN_CL ? ((zc >> 5) * (ROWS * 96) + (yc - (r.y0 - H)) * 96 + 3 * (zc & 31)) : ((yc - (r.y0 - H)) * ZP + zc);
+            own_off[j] = IN_CL == 2 ? ((yc - (r.y0 - H)) * (3 * ZP) + 3 * zc)
+                         : IN_CL == 1 ? ((zc >> 5) * (ROWS * 96) + (yc - (r.y0 - H)) * 96 + 3 * (zc & 31)) : ((yc - (r.y0 - H)) * ZP + zc);
             op[j] = out + (size_t)r.b * 3 * N + ((uint32_t)r.xs * XS + (uint32_t)yc * Z + zc);
         }
         int sb = rslot + (r.xs - H - r.p_first);                       // slot of plane xs - H (in [-H, 0] relative to the run)
@@ -253,7 +258,20 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     if (qA1 == ring_end) qA1 = ring;
                     if (qB1 == ring_end) qB1 = ring;
                     u64_t acc[3];
-                    if (IN_CL) {
+                    if (IN_CL == 2) {
+                        const int offA = ryA * (3 * ZP) + 3 * (izA - 1), offB = ryB * (3 * ZP) + 3 * (izB - 1);
+                        qA0 += offA; qA1 += offA; qB0 += offB; qB1 += offB;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float va[8] = {qA0[c], qA0[3 + c], qA0[3 * ZP + c], qA0[3 * ZP + 3 + c],
+                                                 qA1[c], qA1[3 + c], qA1[3 * ZP + c], qA1[3 * ZP + 3 + c]};
+                            const float vb[8] = {qB0[c], qB0[3 + c], qB0[3 * ZP + c], qB0[3 * ZP + 3 + c],
+                                                 qB1[c], qB1[3 + c], qB1[3 * ZP + c], qB1[3 * ZP + 3 + c]};
+                            acc[c] = mul2(w[0], pk(va[0], vb[0]));
+#pragma unroll
+                            for (int k = 1; k < 8; ++k) acc[c] = fma2(w[k], pk(va[k], vb[k]), acc[c]);
+                        }
+                    } else if (IN_CL == 1) {
                         const int zlA = izA - 1, zlB = izB - 1;
                         const int faA = (zlA >> 5) * (ROWS * 96) + 3 * (zlA & 31) + ryA * 96, fbA = (izA >> 5) * (ROWS * 96) + 3 * (izA & 31) + ryA * 96;
                         const int faB = (zlB >> 5) * (ROWS * 96) + 3 * (zlB & 31) + ryB * 96, fbB = (izB >> 5) * (ROWS * 96) + 3 * (izB & 31) + ryB * 96;
@@ -324,7 +342,16 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     if (q0 >= ring_end) q0 -= R * SLOT;
                     const float *q1 = q0 + SLOT;
                     if (q1 == ring_end) q1 = ring;
-                    if (IN_CL) {
+                    if (IN_CL == 2) {
+                        const int off = ry * (3 * ZP) + 3 * (az.i1 - 1);
+                        q0 += off; q1 += off;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float val[8] = {q0[c], q0[3 + c], q0[3 * ZP + c], q0[3 * ZP + 3 + c],
+                                                  q1[c], q1[3 + c], q1[3 * ZP + c], q1[3 * ZP + 3 + c]};
+                            a[c] = tri_accumulate(w, val);
+                        }
+                    } else if (IN_CL == 1) {
                         const int zl = az.i1 - 1, zh = az.i1;
                         const int fa = (zl >> 5) * (ROWS * 96) + 3 * (zl & 31) + ry * 96, fb = (zh >> 5) * (ROWS * 96) + 3 * (zh & 31) + ry * 96;
                         const float *q0a = q0 + fa, *q0b = q0 + fb, *q1a = q1 + fa, *q1b = q1 + fb;
@@ -411,15 +438,16 @@ static int march_cfg_int(const char *name, int dflt) {
     return c ? atoi(c) : dflt;
 }
 
-template <int TY, int VPT, int H, int R, int NZW, bool IN_CL, bool FIRST>
+template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST>
 static int launch_march_t(const float *src, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
                           MarchSel sel, int seglen, cudaStream_t st) {
     constexpr int ROWS = TY + 2 * H, ZP = NZW * 32;
     constexpr size_t smem = (size_t)R * 3 * ROWS * ZP * sizeof(float);
     static_assert(smem <= 227 * 1024 - 256, "ring does not fit shared memory");
     CUtensorMap tmap;
-    const bool enc = IN_CL ? encode_planar_map(&tmap, src, B, X, Y, 3 * Z, 1, ROWS, 96, 1)
-                           : encode_planar_map(&tmap, src, B * 3, X, Y, Z, 1, ROWS, ZP, 3);
+    const bool enc = IN_CL == 2 ? encode_cl_rows_map(&tmap, src, B, X, Y, Z, ROWS)
+                     : IN_CL == 1 ? encode_planar_map(&tmap, src, B, X, Y, 3 * Z, 1, ROWS, 96, 1)
+                                  : encode_planar_map(&tmap, src, B * 3, X, Y, Z, 1, ROWS, ZP, 3);
     if (!enc) return DFM_EUNSUPPORTED;
     static bool configured = false;
     if (!configured) {
@@ -447,9 +475,14 @@ static int launch_march_t(const float *src, float *out, int B, int X, int Y, int
 template <int TY, int VPT, int H, int R, int NZW>
 static int launch_march_modes(const float *src, float *out, int B, int X, int Y, int Z, float scale, bool in_cl,
                               bool first, float *absmax, MarchSel sel, int seglen, cudaStream_t st) {
-    if (in_cl) return first ? launch_march_t<TY, VPT, H, R, NZW, true, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st) : DFM_EUNSUPPORTED;
-    return first ? launch_march_t<TY, VPT, H, R, NZW, false, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st)
-                 : launch_march_t<TY, VPT, H, R, NZW, false, false>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+    if (in_cl) {
+        if (!first) return DFM_EUNSUPPORTED;
+        static const bool no_rows = getenv("DFM_MARCH_NO_CL_ROWS") != nullptr;                       // tuning aid
+        if (Z == NZW * 32 && !no_rows) return launch_march_t<TY, VPT, H, R, NZW, 2, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+        return launch_march_t<TY, VPT, H, R, NZW, 1, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+    }
+    return first ? launch_march_t<TY, VPT, H, R, NZW, 0, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st)
+                 : launch_march_t<TY, VPT, H, R, NZW, 0, false>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
 }
 
 bool ss_march_eligible(const float *src, int X, int Y, int Z) {

@@ -36,6 +36,18 @@ bool encode_planar_map(CUtensorMap *tmap, const float *base, int nvol, int X, in
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool encode_cl_rows_map(CUtensorMap *tmap, const float *base, int B, int X, int Y, int Z, int rows) {
+    if (!encode_fn() || Z % 32 != 0) return false;
+    const cuuint64_t row = (cuuint64_t)Z * 3 * 4;
+    const cuuint64_t dims[5] = {96, (cuuint64_t)(3 * Z / 96), (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {96 * 4, row, row * (cuuint64_t)Y, row * (cuuint64_t)Y * (cuuint64_t)X};
+    const cuuint32_t box[5] = {96, (cuuint32_t)(3 * Z / 96), (cuuint32_t)rows, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return encode_fn()(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void *)base, dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool tma_planar_ok(const float *p, int X, int Y, int Z) {
     (void)X; (void)Y;
     return encode_fn() != nullptr && Z % 4 == 0 && aligned16(p);

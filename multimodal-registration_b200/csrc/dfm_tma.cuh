@@ -40,9 +40,21 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tmap, 
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
 // 4-D map over a planar [nvol][X][Y][Z] fp32 tensor with box {bz, by, bx, bc}  -- dfm_tma.cu
 bool encode_planar_map(CUtensorMap *tmap, const float *base, int nvol, int X, int Y, int Z, int bx, int by, int bz,
                        int bc);
+// 5-D map over a channels-last 3-component field [B][X][Y][Z][3] whose rows (3 Z floats, Z a multiple of 32) are split in
+// 96-float pieces: dims {96, 3Z/96, Y, X, B}, box {96, 3Z/96, rows, 1, 1} -- a box lands as `rows` contiguous rows of 3 Z floats
+bool encode_cl_rows_map(CUtensorMap *tmap, const float *base, int B, int X, int Y, int Z, int rows);
 // TMA needs a 16-byte aligned base and 16-byte multiples for every global stride
 bool tma_planar_ok(const float *p, int X, int Y, int Z);
 
