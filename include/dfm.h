@@ -106,6 +106,17 @@ int dfm_rescale_warp_fwd(const float *img, const float *coarse, float *out, cons
                          const float *cz, float *work, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh,
                          int X, int Y, int Z, float factor, int has_fill, float fill, void *stream);
 
+/* The same fusion for NEAREST-neighbour warps of one-channel volumes of 4-byte elements (label maps and
+ * segmentations: Transform(interp_method='nearest', rescale=scale) at 3d_reg.py:377-380,
+ * bids_registration.py:380-383, bids_two_steps_registration.py:338-341,354-355): U is marched like
+ * dfm_resize_fwd's up-sampler and each output picks img at round-half-even(p + U), clipped; values are
+ * moved as raw bits (fill_bits: the 32-bit fill pattern).  Bit-identical to dfm_resize_fwd followed by
+ * dfm_warp_fwd(DFM_NEAREST) in both builds.  work as in dfm_rescale_warp_fwd. */
+int dfm_rescale_warp_nearest_fwd(const void *img, const float *coarse, void *out, const float *cx, const float *cy,
+                                 const float *cz, float *work, int B, int Xi, int Yi, int Zi, int Xh, int Yh,
+                                 int Zh, int X, int Y, int Z, float factor, int has_fill, uint32_t fill_bits,
+                                 void *stream);
+
 /* Backward of the linear warp (TensorFlow autodiff semantics of the reference graph:
  * floor has zero gradient, clip passes gradient inside [0, max] inclusive).
  *   gimg   (nullable): [B,C,Xi,Yi,Zi] is ACCUMULATED INTO (caller zeroes it).

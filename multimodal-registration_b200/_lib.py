@@ -25,6 +25,7 @@ SIGNATURES = {
     'dfm_warp_fwd': (_i, [_p, _p, _p] + [_i] * 8 + [_i, _i, _i, _f, _u64, _u, _p]),
     'dfm_warp_channelwise_fwd': (_i, [_p, _p, _p] + [_i] * 9 + [_f, _i, _p]),
     'dfm_rescale_warp_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _f, _p]),
+    'dfm_rescale_warp_nearest_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _c.c_uint32, _p]),
     'dfm_warp_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
     'dfm_field_warp_add': (_i, [_p, _p, _p] + [_i] * 7 + [_f, _i, _u, _p]),
     'dfm_vecint_workspace_bytes': (_z, [_i] * 6),

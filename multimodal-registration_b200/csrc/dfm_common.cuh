@@ -83,6 +83,10 @@ int launch_rescale_warp_tex(const float *img, const float *half, float *out, con
                             const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
                             float pre, int has_fill, float fill, cudaStream_t st);
 
+// fused RescaleTransform + one-channel NEAREST warp of 4-byte elements on the same march (no textures) -- dfm_warp_tex.cu
+int launch_rescale_warp_nearest(const void *img, const float *half, void *out, const float *cx, const float *cy,
+                                const float *cz, int B, int Xi, int Yi, int Zi, int Xh, int Yh, int Zh, int X, int Y, int Z,
+                                float pre, int has_fill, uint32_t fill_bits, cudaStream_t st);
 // stand-alone one-channel linear warp by texture gathers -- dfm_warp_tex.cu (DFM_EUNSUPPORTED if not applicable / not selected)
 int launch_warp_tex(const float *img, const float *field, float *out, int B, int Xi, int Yi, int Zi, int X, int Y, int Z,
                     int has_fill, float fill, unsigned flags, cudaStream_t st);

@@ -347,3 +347,25 @@ extern "C" int dfm_rescale_warp_fwd(const float *img, const float *coarse, float
     if (rc) return rc;
     return dfm_warp_fwd(img, work, out, B, 1, Xi, Yi, Zi, X, Y, Z, DFM_LINEAR, 4, has_fill, fill, 0, 0u, stream);
 }
+
+extern "C" int dfm_rescale_warp_nearest_fwd(const void *img, const float *coarse, void *out, const float *cx, const float *cy,
+                                            const float *cz, float *work, int B, int Xi, int Yi, int Zi, int Xh, int Yh,
+                                            int Zh, int X, int Y, int Z, float factor, int has_fill, uint32_t fill_bits,
+                                            void *stream) {
+    DFM_REQUIRE(B >= 0 && Xi >= 1 && Yi >= 1 && Zi >= 1 && Xh >= 1 && Yh >= 1 && Zh >= 1 && X >= 1 && Y >= 1 && Z >= 1,
+                DFM_EINVAL, "dfm_rescale_warp_nearest_fwd: bad shape");
+    DFM_REQUIRE(B <= 65535 && X <= 65535, DFM_EINVAL, "dfm_rescale_warp_nearest_fwd: B and X must be <= 65535");
+    DFM_REQUIRE((uint64_t)X * Y * Z < (1ull << 30) && (uint64_t)Xi * Yi * Zi < (1ull << 30), DFM_EINVAL,
+                "dfm_rescale_warp_nearest_fwd: volume too large (>= 2^30 voxels)");
+    DFM_REQUIRE(factor >= 1.f, DFM_EINVAL, "dfm_rescale_warp_nearest_fwd: factor %g < 1 (scale-then-resize order only)", factor);
+    if (B == 0) return DFM_OK;
+    DFM_REQUIRE(img && coarse && out && cx && cy && cz, DFM_EINVAL, "dfm_rescale_warp_nearest_fwd: null pointer");
+    DFM_REQUIRE(img != out, DFM_EINVAL, "dfm_rescale_warp_nearest_fwd: out must not alias img");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_rescale_warp_nearest(img, coarse, out, cx, cy, cz, B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, factor, has_fill, fill_bits, st);
+    if (rc != DFM_EUNSUPPORTED) return rc;
+    DFM_REQUIRE(work, DFM_EUNSUPPORTED, "dfm_rescale_warp_nearest_fwd: fused kernel not applicable to this shape and no work buffer given");
+    rc = dfm_resize_fwd(coarse, work, cx, cy, cz, B, 3, Xh, Yh, Zh, X, Y, Z, factor, 1.f, DFM_LINEAR, 0u, stream);
+    if (rc) return rc;
+    return dfm_warp_fwd(img, work, out, B, 1, Xi, Yi, Zi, X, Y, Z, DFM_NEAREST, 4, has_fill, 0.f, (uint64_t)fill_bits, 0u, stream);
+}

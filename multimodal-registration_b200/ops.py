@@ -439,18 +439,24 @@ def rescale_dense_transform(trf, factor, interp_method=LINEAR, out_layout='plana
     return resize(trf, factor, interp_method, pre=factor, post=1.0, out_layout=out_layout)
 
 
-def rescale_warp(img, coarse_field, factor, fill_value=None):
-    """Fused ``RescaleTransform(factor)`` + linear ``SpatialTransformer`` of a one-channel image
-    (dfm.h: dfm_rescale_warp_fwd): the result of rescale_dense_transform followed by warp (bit-identical in
-    the exact build, separable evaluation within a few ulp in the default build) without materialising
-    the full-resolution field.  Inference only (no autograd)."""
+def rescale_warp(img, coarse_field, factor, fill_value=None, interp_method=LINEAR):
+    """Fused ``RescaleTransform(factor)`` + ``SpatialTransformer`` of a one-channel image (dfm.h: dfm_rescale_warp_fwd,
+    dfm_rescale_warp_nearest_fwd): the result of rescale_dense_transform followed by warp -- bit-identical wherever the
+    marching kernels apply, within a few ulp of it in the default build otherwise -- without materialising the
+    full-resolution field.  'nearest' moves 4-byte elements (float32 / int32 label maps).  Inference only (no autograd)."""
     _require_cuda(img, 'img')
     coarse_field = _check_field(coarse_field, 'coarse_field')
     if img.dim() != 5 or img.shape[-1] != 1:
         raise ValueError('rescale_warp: img must be [B, X, Y, Z, 1]')
     if factor < 1:
         raise ValueError('rescale_warp: factor must be >= 1')
-    img = img.float().contiguous()
+    nearest = _interp_code(interp_method) == _lib.DFM_NEAREST
+    if nearest:
+        if img.element_size() != 4:
+            img = img.float()
+        img = img.contiguous()
+    else:
+        img = img.float().contiguous()
     coarse = to_layout(coarse_field.detach(), 'planar')
     B, Xi, Yi, Zi, _ = img.shape
     _, Xh, Yh, Zh, _ = coarse.shape
@@ -459,17 +465,24 @@ def rescale_warp(img, coarse_field, factor, fill_value=None):
     cx = _coords.device_tables(Xh, X, dev)[0]
     cy = _coords.device_tables(Yh, Y, dev)[0]
     cz = _coords.device_tables(Zh, Z, dev)[0]
-    out = torch.empty((B, X, Y, Z, 1), device=img.device, dtype=torch.float32)
+    out = torch.empty((B, X, Y, Z, 1), device=img.device, dtype=img.dtype)
     has_fill = fill_value is not None
+    if nearest:
+        fill_arg = int.from_bytes(torch.tensor([fill_value if has_fill else 0]).to(img.dtype).numpy().tobytes(), 'little')
+        name = 'dfm_rescale_warp_nearest_fwd'
+    else:
+        fill_arg = float(fill_value or 0.0)
+        name = 'dfm_rescale_warp_fwd'
+
+    def call(work):
+        _lib.call(name, _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(work),
+                  B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), fill_arg, _stream())
     try:
-        _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(None),
-                  B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())
+        call(None)
     except _lib.DfmError as e:
         if e.code != _lib.DFM_EUNSUPPORTED:               # only "shape not covered by the fused kernel" falls back
             raise
-        work = torch.empty(B * 3 * X * Y * Z, device=img.device, dtype=torch.float32)
-        _lib.call('dfm_rescale_warp_fwd', _ptr(img), _ptr(coarse), _ptr(out), _ptr(cx), _ptr(cy), _ptr(cz), _ptr(work),
-                  B, Xi, Yi, Zi, Xh, Yh, Zh, X, Y, Z, float(factor), int(has_fill), float(fill_value or 0.0), _stream())
+        call(torch.empty(B * 3 * X * Y * Z, device=img.device, dtype=torch.float32))
     return out
 
 

@@ -44,11 +44,11 @@ class Transform(torch.nn.Module):
         self._check(scan, trf)
         if self.rescaler is not None:
             tr = self.transformer
-            fusable = (tr.interp_method == 'linear' and self.rescale >= 1 and self.nb_feats == 1 and tr.indexing == 'ij' and
-                       not tr.single_transform and
+            fusable = (tr.interp_method in ('linear', 'nearest') and self.rescale >= 1 and self.nb_feats == 1 and
+                       tr.indexing == 'ij' and not tr.single_transform and
                        not (torch.is_grad_enabled() and (scan.requires_grad or trf.requires_grad)))
-            if fusable:        # the rescaled field is an intermediate: one kernel (dfm_rescale_warp_fwd), same result
-                return ops.rescale_warp(scan, trf, self.rescale, tr.fill_value)
+            if fusable:        # the rescaled field is an intermediate: one kernel (dfm_rescale_warp*_fwd), same result
+                return ops.rescale_warp(scan, trf, self.rescale, tr.fill_value, tr.interp_method)
             trf = self.rescaler(trf)
         return self.transformer([scan, trf])
 

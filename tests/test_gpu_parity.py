@@ -456,6 +456,32 @@ def test_fused_texture_gather_path():
                 assert np.mean(~np.isclose(fused, want, rtol=RTOL, atol=ATOL)) < 1e-3
 
 
+def test_fused_rescale_nearest_warp():
+    """dfm_rescale_warp_nearest_fwd (label maps through Transform(interp_method='nearest', rescale=2), 3d_reg.py:377-380):
+    the same bits as the two stand-alone kernels and as the oracle, float32 and int32 labels, fill values, shapes the
+    marching kernel covers and one it does not (work-buffer fallback)."""
+    rng = np.random.default_rng(614)
+    for shape, B, factor, fv, dt in [((8, 12, 16), 2, 2, None, np.float32), ((9, 11, 20), 1, 2, 0, np.float32),
+                                     ((8, 12, 16), 33, 2, 7, np.int32), ((6, 5, 7), 1, 2, 0, np.float32),
+                                     ((20, 24, 40), 2, 2, None, np.int32)]:
+        full = tuple(int(s * factor) for s in shape)
+        half = smooth_noise(rng, (B,) + shape + (3,), 2.5, smooth=1)
+        labels = rng.integers(0, 26, (B,) + full + (1,)).astype(dt)
+        d_lab, d_half = dev(labels), dev(half, 'planar')
+        fused = host(ops.rescale_warp(d_lab, d_half, factor, fv, 'nearest'))
+        assert fused.dtype == dt
+        unfused = host(ops.warp(d_lab, ops.rescale_dense_transform(d_half, factor), 'nearest', fv))
+        np.testing.assert_array_equal(fused, unfused)
+        if B <= 2 and mrb._lib.exact_order():          # the default build's up-sampler is a few ulp off: ties may round the other way
+            np.testing.assert_array_equal(fused, io.spatial_transformer(labels, io.rescale_dense_transform(half, factor), 'nearest', fv))
+    # through the model mirror
+    scan = rng.integers(0, 5, (2, 16, 24, 32, 1)).astype(np.float32)
+    half = smooth_noise(rng, (2, 8, 12, 16, 3), 2.0, smooth=1)
+    got = vxm.networks.Transform((16, 24, 32), interp_method='nearest', rescale=2).predict([scan, half])
+    want = host(ops.warp(dev(scan), ops.rescale_dense_transform(dev(half, 'planar'), 2), 'nearest'))
+    np.testing.assert_array_equal(got, want)
+
+
 def test_fused_texture_gather_is_reproducible():
     """The coarse-plane ring of the fused kernel is released by data-dependent arrivals (a consumer's arrival must not
     overtake its shared loads): many launches at a size with thousands of CTAs give the same bits every time."""
