@@ -68,8 +68,8 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
         with torch.no_grad():
             maps = []
             for k in range(2):
-                w = ops.rescale_dense_transform(ops.vecint(vel[k], STEPS), 2)
-                maps.append(ops.warp(labels[k], w, 'nearest', fill_value=0))
+                # VecInt -> RescaleTransform(2) -> nearest warp; the full-resolution field is an intermediate (fused kernel)
+                maps.append(ops.rescale_warp(labels[k], ops.vecint(vel[k], STEPS), 2, 0, 'nearest'))
         flow = flow_full.detach().requires_grad_(True)            # what the flow convolution emits (full res)
         svf = ops.rescale_dense_transform(flow, 0.5)
         pos = ops.rescale_dense_transform(ops.vecint(svf, STEPS), 2)

@@ -54,13 +54,14 @@ def measure(rank, world, dev, subjects=64, steps=5, warmup=3):
     seg = torch.randint(0, 26, (B, *FULL, 1), generator=g).float().to(dev)
     model1 = networks.VxmDense(FULL, int_steps=INT_STEPS, svf_resolution=2, int_resolution=2)
     model2 = networks.VxmDense(FULL, int_steps=INT_STEPS, svf_resolution=2, int_resolution=2)
-    tr_seg = networks.Transform(FULL, interp_method='nearest', rescale=2)
 
     def step():
         with torch.no_grad():
             res = pipelines.two_steps_tail(moving, fixed, model1, model2, flow1, flow2, 'linear')    # :316-324
-            moved_seg = tr_seg([seg, res['warp']])                    # nearest variant of the final transform (:338-355)
             saved = ops.rescale_dense_transform(res['warp'], res['scale'], out_layout='cl')          # :515
+            # nearest variant of the final transform (:338-355, Transform(nearest, rescale=scale)): the rescaled warp is
+            # needed for the export anyway, so the label warp reads it instead of re-deriving it inside a fused kernel
+            moved_seg = ops.warp(seg, saved, 'nearest')
         return res['moved'], moved_seg, saved
 
     for _ in range(warmup):
