@@ -105,7 +105,9 @@ __device__ __forceinline__ void exact_field(const float (&V)[2][3][2][3], const 
 // 72 registers -> 3 CTAs (24 consumer warps) per SM.  Measured at B=32 (160x160x192): 0.727 ms; a software-pipelined variant
 // (the gathers of plane x+1 issued before the results of plane x are consumed: 96 registers, 2 CTAs/SM) 0.93 ms, 4 CTAs/SM at
 // 56 registers 0.728 ms -- resident warps, not gathers in flight per thread, hide the texture latency.  A hybrid that
-// fetched the upper x plane's four corners with LDG (L1 hits) to relieve the texture write-back: 0.85 ms (slower).
+// fetched the upper x plane's four corners with LDG (L1 hits) to relieve the texture write-back: 0.85 ms (slower).  The
+// stand-alone up-sampler's __syncthreads() per coarse plane instead of the producer warp and per-warp releases: 0.80 ms
+// (with gathers in flight a block barrier makes every warp wait for the slowest one's texture latency).
 // NEAREST: the same march with a nearest-neighbour pick of a 4-byte image element (label maps: Transform(interp_method='nearest',
 // rescale=2), 3d_reg.py:377-380) -- one plain load per voxel, values moved as raw bits, no texture involved.  Measured (B=32):
 // 0.67 ms against 0.39 + 0.47 ms for the up-sampler and the stand-alone nearest warp; issue-bound (61 % busy: the march and the
