@@ -82,6 +82,27 @@ def main():
             if min(int(s * factor) for s in shape) >= 1:
                 want = io.rescale_dense_transform(field, factor)
                 fails += not check('rescale x%g %s' % (factor, tag), host(ops.rescale_dense_transform(dev(field, fl), factor)), want, exact)
+            if factor >= 1 and min(int(s * factor) for s in shape) >= 1:
+                # fused RescaleTransform + warp of a one-channel image (texture-gather / marching kernels where the shapes allow,
+                # the brick fusion or the two-kernel fallback otherwise): against the chained oracle and the unfused kernels
+                full = tuple(int(s * factor) for s in shape)
+                ishape = full if rng.random() < 0.7 else tuple(int(rng.integers(2, maxd + 1)) for _ in range(3))
+                img1 = rng.random((B,) + ishape + (1,)).astype(np.float32)
+                lab1 = rng.integers(0, 9, (B,) + ishape + (1,)).astype(np.float32)
+                d_half = dev(field, 'planar')
+                up = ops.rescale_dense_transform(d_half, factor)
+                want = io.spatial_transformer(img1, io.rescale_dense_transform(field, factor), 'linear', fill)
+                got = host(ops.rescale_warp(dev(img1), d_half, factor, fill))
+                if fill is None or exact:
+                    fails += not check('fused rescale+warp x%g %s' % (factor, tag), got, want, exact)
+                elif np.mean(~np.isclose(got, want, rtol=RTOL, atol=ATOL)) >= 1e-3:      # a few-ulp flow change can flip a voxel across the fill boundary
+                    print('MISMATCH fused rescale+warp (fill)', tag)
+                    fails += 1
+                got_nn = host(ops.rescale_warp(dev(lab1), d_half, factor, fill, 'nearest'))
+                fails += not check('fused rescale+nearest x%g %s' % (factor, tag), got_nn, host(ops.warp(dev(lab1), up, 'nearest', fill)), True)
+                if exact:
+                    fails += not check('fused rescale+nearest vs oracle x%g %s' % (factor, tag), got_nn,
+                                       io.spatial_transformer(lab1, io.rescale_dense_transform(field, factor), 'nearest', fill), True)
             if min(shape) >= 5:
                 det, stats = ops.jacobian_determinant(dev(field, fl), out_dtype=torch.float64)
                 want = np.stack([jo.jacobian_determinant(field[i][:, :, :, None, :].astype(np.float64))[0] for i in range(B)])
