@@ -117,6 +117,20 @@ int dfm_rescale_warp_nearest_fwd(const void *img, const float *coarse, void *out
                                  int Zh, int X, int Y, int Z, float factor, int has_fill, uint32_t fill_bits,
                                  void *stream);
 
+/* Linear warp of a ONE-HOT label map straight from the label map (forward and d/d field):
+ *   replaces: pred = vxm.layers.SpatialTransformer(interp_method='linear')([map_1, flow]) at train_synthmorph.py:298,
+ *             where map_1 is the one-hot output of ne.models.labels_to_image (:288-289) -- one-hot by construction.
+ *   labels [B][Xi][Yi][Zi] uint8 (values >= C act as an all-zero row), field [B][3][X][Y][Z] (or channels-last,
+ *   DFM_FIELD_IN_CL), out / gout [B][X][Y][Z][C] channels-last (the reference layout), C <= 256.
+ *   out[b,p,c] = sum of the trilinear corner weights whose corner label is c, accumulated in corner order: bit-identical
+ *   to dfm_warp_fwd on the materialised one-hot tensor (DFM_IMG_CL) in both builds, without building or reading it.
+ *   dfm_warp_onehot_bwd: gfield [B][3][X][Y][Z] (DFM_FIELD_OUT_CL: channels-last) is overwritten with d/d field of
+ *   sum(gout * out) (TensorFlow autodiff semantics as dfm_warp_bwd; labels carry no gradient); C <= 48. */
+int dfm_warp_onehot_fwd(const uint8_t *labels, const float *field, float *out, int B, int C, int Xi, int Yi, int Zi,
+                        int X, int Y, int Z, int has_fill, float fill, unsigned flags, void *stream);
+int dfm_warp_onehot_bwd(const float *gout, const uint8_t *labels, const float *field, float *gfield, int B, int C,
+                        int Xi, int Yi, int Zi, int X, int Y, int Z, int has_fill, unsigned flags, void *stream);
+
 /* Backward of the linear warp (TensorFlow autodiff semantics of the reference graph:
  * floor has zero gradient, clip passes gradient inside [0, max] inclusive).
  *   gimg   (nullable): [B,C,Xi,Yi,Zi] is ACCUMULATED INTO (caller zeroes it).

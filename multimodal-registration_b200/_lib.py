@@ -26,6 +26,8 @@ SIGNATURES = {
     'dfm_warp_channelwise_fwd': (_i, [_p, _p, _p] + [_i] * 9 + [_f, _i, _p]),
     'dfm_rescale_warp_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _f, _p]),
     'dfm_rescale_warp_nearest_fwd': (_i, [_p] * 7 + [_i] * 10 + [_f, _i, _c.c_uint32, _p]),
+    'dfm_warp_onehot_fwd': (_i, [_p, _p, _p] + [_i] * 8 + [_i, _f, _u, _p]),
+    'dfm_warp_onehot_bwd': (_i, [_p] * 4 + [_i] * 8 + [_i, _u, _p]),
     'dfm_warp_bwd': (_i, [_p] * 5 + [_i] * 8 + [_i, _u, _p]),
     'dfm_field_warp_add': (_i, [_p, _p, _p] + [_i] * 7 + [_f, _i, _u, _p]),
     'dfm_vecint_workspace_bytes': (_z, [_i] * 6),

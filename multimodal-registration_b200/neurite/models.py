@@ -122,6 +122,14 @@ class LabelsToImage:
         lut = torch.from_numpy(self._lut_host).to(dev)
         onehot = torch.empty((B, X, Y, Z, C), device=dev, dtype=torch.float32)
         _lib.call('dfm_onehot', _ptr(warped), _ptr(lut), int(lut.numel()), C, _ptr(onehot), B * n, _stream())
+        if C <= 255:
+            # the map is one-hot by construction: it carries its channel indices (255 = no channel) so that the
+            # SpatialTransformer that produces `pred` (train_synthmorph.py:298) can warp it from 8 bytes per voxel instead of
+            # 8 x C floats (ops.warp_onehot, same bits).  Any tensor operation on the map yields a plain tensor without them.
+            lab = warped[..., 0].long()
+            idx = lut.long()[lab.clamp(0, lut.numel() - 1)]
+            ok = (lab >= 0) & (lab < lut.numel()) & (idx >= 0) & (idx < C)
+            onehot.dfm_labels = (torch.where(ok, idx, torch.full_like(idx, 255)).to(torch.uint8), C)
         outs = [img[..., None], onehot]
         if self.return_def:
             outs.append(flow)

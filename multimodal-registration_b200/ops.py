@@ -219,6 +219,74 @@ def warp(img, field, interp_method=LINEAR, fill_value=None, loc_absolute=False):
     return _warp_fwd_raw(img.detach(), field.detach(), NEAREST, fill_value, loc_absolute)
 
 
+class _WarpOneHot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels_u8, field, C, fill_value):
+        B, Xi, Yi, Zi = labels_u8.shape
+        _, X, Y, Z, _ = field.shape
+        field, f_cl = _field_layout(field, 'field')
+        out = torch.empty((B, X, Y, Z, C), device=field.device, dtype=torch.float32)
+        has_fill = fill_value is not None
+        _lib.call('dfm_warp_onehot_fwd', _ptr(labels_u8), _ptr(field), _ptr(out), B, C, Xi, Yi, Zi, X, Y, Z,
+                  int(has_fill), float(fill_value or 0.0), _lib.FIELD_IN_CL if f_cl else 0, _stream())
+        ctx.save_for_backward(labels_u8, field)
+        ctx.C, ctx.has_fill, ctx.f_cl = C, has_fill, f_cl
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        labels_u8, field = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None, None, None
+        B, Xi, Yi, Zi = labels_u8.shape
+        _, X, Y, Z, _ = field.shape
+        gout = gout.float().contiguous()
+        gfield = empty(field.shape, 'planar', field.device)
+        _lib.call('dfm_warp_onehot_bwd', _ptr(gout), _ptr(labels_u8), _ptr(field), _ptr(gfield), B, ctx.C, Xi, Yi, Zi,
+                  X, Y, Z, int(ctx.has_fill), _lib.FIELD_IN_CL if ctx.f_cl else 0, _stream())
+        return None, gfield, None, None
+
+
+ONEHOT_BWD_CMAX = 48
+
+
+def warp_onehot(labels, field, num_labels, fill_value=None):
+    """``warp(one_hot(labels, num_labels), field)`` -- the ``pred`` of train_synthmorph.py:298, whose first input is the one-hot
+    map a ``labels_to_image`` generator emits -- computed from the LABEL MAP (dfm.h: dfm_warp_onehot_fwd / _bwd): a corner of a
+    one-hot map is its label, so a voxel gathers 8 bytes instead of 8 x C floats and the one-hot tensor is never built.
+    Bit-identical to the generic warp on the materialised tensor; differentiable with respect to ``field``.
+    labels [B, X, Y, Z] or [B, X, Y, Z, 1], integer valued (any dtype); returns channels-last [B, X, Y, Z, num_labels]."""
+    _require_cuda(labels, 'labels')
+    field = _check_field(field, 'field')
+    if labels.dim() == 5:
+        if labels.shape[-1] != 1:
+            raise ValueError('warp_onehot: labels must be [B, X, Y, Z] or [B, X, Y, Z, 1], got %s' % (tuple(labels.shape),))
+        labels = labels[..., 0]
+    if labels.dim() != 4 or labels.shape[0] != field.shape[0]:
+        raise ValueError('warp_onehot: labels %s do not match field %s' % (tuple(labels.shape), tuple(field.shape)))
+    C = int(num_labels)
+    if not 1 <= C <= 256:
+        raise ValueError('warp_onehot: num_labels must be in 1..256')
+    lab = labels.detach()
+    if lab.dtype != torch.uint8:
+        lab = lab.clamp(0, 255).to(torch.uint8)       # values >= num_labels are all-zero rows, like a label outside the list
+    lab = lab.contiguous()
+    needs_grad = torch.is_grad_enabled() and field.requires_grad
+    if needs_grad and C > ONEHOT_BWD_CMAX:            # the adjoint kernel stages a [256, C] gradient tile in shared memory
+        onehot = torch.nn.functional.one_hot(lab.long(), 256)[..., :C].float()
+        return warp(onehot, field, LINEAR, fill_value)
+    if needs_grad:
+        return _WarpOneHot.apply(lab, field, C, fill_value)
+    return _WarpOneHot.forward(_NoCtx(), lab, field.detach(), C, fill_value)
+
+
+class _NoCtx:
+    """Stand-in for the autograd context when no gradient is needed."""
+
+    def save_for_backward(self, *a):
+        pass
+
+
 def warp_channelwise(img, field, interp_method=LINEAR, fill_value=None, argmax=False):
     """Channel-wise transform: field [B, X, Y, Z, C, 3] carries one 3-vector per channel
     (``vxm.utils.transform`` as called at train_synthmorph.py:67).  Linear interpolation runs one kernel that

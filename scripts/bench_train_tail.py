@@ -62,6 +62,7 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
     # (outside the hot path) and the upstream gradient of `pred` comes from the Dice loss
     onehot_cl = torch.nn.functional.one_hot(labels[0][..., 0].long(), C).float()   # channels-last, like the reference
     gpred = torch.rand(B, *FULL, C, generator=g).to(dev)                             # channels-last too
+    labels_u8 = None if os.environ.get('DFM_TRAIN_GENERIC_PRED') else labels[0][..., 0].to(torch.uint8)   # what the generator attaches to its map
 
     def step():
         # generators (no gradient)
@@ -75,7 +76,9 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
         pos = ops.rescale_dense_transform(ops.vecint(svf, STEPS), 2)
         with torch.no_grad():
             y_source = ops.warp(image, pos.detach())
-        pred = ops.warp(onehot_cl, pos)                           # channels-last in and out (dfm_warp_cl.cu)
+        # pred = SpatialTransformer('linear')([map_1, flow]): map_1 is the generator's one-hot map, warped from its label map
+        # (ops.warp_onehot: the same bits as the generic channels-last warp of the one-hot tensor, 8 bytes gathered per voxel)
+        pred = ops.warp_onehot(labels_u8, pos, C) if labels_u8 is not None else ops.warp(onehot_cl, pos)
         pred.backward(gpred)
         sharding.allreduce_mean_(unet_grad)                       # the step's only collective
         return flow.grad, y_source
@@ -102,7 +105,8 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
     return {'workload': 'train_synthmorph.py step, deformation hot path fwd+bwd (config/config.json shapes)',
             'n_gpus': world, 'items_per_gpu': B, 'ms_per_step': ms, 'items_per_s': world * B / (ms * 1e-3),
             'algorithmic_GB_per_item': (FWD + BWD) / 1e9, 'aggregate_GBps': gbs, 'frac_of_peak_per_gpu': gbs / world / peak,
-            'includes': '26-channel map and its gradient in the reference channels-last layout (no conversion), 5.79 MB NCCL all-reduce',
+            'includes': '26-channel pred and its gradient in the reference channels-last layout, computed from the one-hot map\'s label map '
+                        '(dfm_warp_onehot_fwd / _bwd; DFM_TRAIN_GENERIC_PRED=1: generic channels-last kernels), 5.79 MB NCCL all-reduce',
             'scaling': 'weak'}
 
 

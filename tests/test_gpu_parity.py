@@ -394,6 +394,45 @@ def test_fused_rescale_warp_matches_unfused_bitwise():
             assert_linear_parity(fused, io.spatial_transformer(scan, io.rescale_dense_transform(half, 2), 'linear', fv))
 
 
+def test_warp_onehot_equals_generic_warp_of_the_onehot_tensor():
+    """dfm_warp_onehot_fwd / _bwd (pred of train_synthmorph.py:298 from the label map): the forward pass carries the same bits
+    as the generic channels-last warp of the materialised one-hot tensor (both builds), the field gradient agrees with the
+    generic adjoint and with fp64 autograd of the oracle; fill values, channels-last fields, label volume larger than the grid."""
+    rng = np.random.default_rng(615)
+    for shape, B, C, fv, lshape, lay in [((8, 12, 16), 2, 26, None, None, 'planar'), ((9, 7, 13), 1, 5, 0.0, None, 'cl'),
+                                         ((8, 12, 16), 3, 26, -1.0, (11, 12, 20), 'planar'), ((20, 20, 48), 1, 40, None, None, 'cl')]:
+        flow = smooth_noise(rng, (B,) + shape + (3,), 2.5, smooth=1)
+        labels = rng.integers(0, C, (B,) + (lshape or shape)).astype(np.int64)
+        onehot = np.eye(C, dtype=np.float32)[labels]
+        d_lab = torch.from_numpy(labels).cuda()
+        d_flow = dev(flow, lay).requires_grad_(True)
+        got = ops.warp_onehot(d_lab, d_flow, C, fv)
+        d_flow2 = dev(flow, lay).requires_grad_(True)
+        ref = ops.warp(dev(onehot), d_flow2, 'linear', fv)
+        np.testing.assert_array_equal(host(got.detach()), host(ref.detach()))
+        assert_linear_parity(host(got.detach()), io.spatial_transformer(onehot, flow, 'linear', fv))
+        g = torch.from_numpy(rng.standard_normal(tuple(got.shape)).astype(np.float32)).cuda()
+        got.backward(g)
+        ref.backward(g)
+        np.testing.assert_allclose(host(d_flow.grad), host(d_flow2.grad), rtol=1e-4, atol=1e-4 * float(np.abs(host(d_flow2.grad)).max()))
+    # more labels than the shared output tile holds: the per-element kernel (forward only; gradients take the generic path)
+    lab60 = rng.integers(0, 60, (1, 8, 12, 16)).astype(np.int64)
+    flow60 = dev(smooth_noise(rng, (1, 8, 12, 16, 3), 2.0, smooth=1))
+    with torch.no_grad():
+        assert torch.equal(ops.warp_onehot(torch.from_numpy(lab60).cuda(), flow60, 60, 0.5),
+                           ops.to_layout(ops.warp(dev(np.eye(60, dtype=np.float32)[lab60]), flow60, 'linear', 0.5), 'cl'))
+    f60 = flow60.clone().requires_grad_(True)
+    ops.warp_onehot(torch.from_numpy(lab60).cuda(), f60, 60).sum().backward()
+    assert torch.isfinite(f60.grad).all()
+    # no-grad path and label dtypes
+    lab = rng.integers(0, 26, (2, 8, 12, 16, 1)).astype(np.float32)
+    flow = dev(smooth_noise(rng, (2, 8, 12, 16, 3), 2.0, smooth=1))
+    with torch.no_grad():
+        a = ops.warp_onehot(dev(lab), flow, 26)
+        b = ops.warp(dev(np.eye(26, dtype=np.float32)[lab[..., 0].astype(np.int64)]), flow)
+    assert torch.equal(a, ops.to_layout(b, 'cl'))
+
+
 class warp_kernel:
     """Select the one-channel linear warp kernel for the calls inside: 'tex' (texture gathers, the default where the
     image qualifies) or 'brick' (TMA bounding-box brick); the library reads DFM_WARP_TEX per call."""

@@ -109,3 +109,28 @@ def test_labels_to_image_generator():
     sub = mrb.neurite.models.labels_to_image(**dict(gen_args, out_label_list=[1, 3]), seeds={'all': 5})
     _, oh2 = sub.predict(labels)
     assert oh2.shape[-1] == 2 and oh2.sum() > 0 and (oh2.sum(-1) == 0).any()
+
+
+def test_generator_onehot_map_is_warped_from_its_label_map():
+    """pred = SpatialTransformer('linear')([map_1, flow]) (train_synthmorph.py:298) on the generator's one-hot output takes the
+    label-map kernel (ops.warp_onehot); a plain copy of the same tensor takes the generic channels-last kernel: same bits,
+    same field gradient, also with an out_label_list that drops labels (all-zero rows)."""
+    rng = np.random.default_rng(9)
+    shape = (16, 24, 32)
+    labels = rng.integers(0, 6, (2,) + shape + (1,)).astype(np.float32)
+    for out_list in (None, [1, 3, 4]):
+        gen = mrb.neurite.models.labels_to_image(in_shape=shape, in_label_list=list(range(6)), out_label_list=out_list, warp_std=2.0,
+                                                 warp_res=[8], blur_std=1.0, bias_std=0.3, bias_res=[16], gamma_std=0.1, seeds={'all': 3})
+        _, onehot = gen(labels)
+        assert hasattr(onehot, 'dfm_labels') and onehot.dfm_labels[1] == onehot.shape[-1]
+        flow = (rng.standard_normal((2,) + shape + (3,)) * 1.5).astype(np.float32)
+        layer = mrb.voxelmorph.layers.SpatialTransformer(interp_method='linear')
+        f1 = torch.from_numpy(flow).cuda().requires_grad_(True)
+        f2 = torch.from_numpy(flow).cuda().requires_grad_(True)
+        fast = layer([onehot, f1])
+        plain = layer([onehot.clone(), f2])                       # a copy does not carry the label map
+        assert torch.equal(fast, plain)
+        g = torch.from_numpy(rng.standard_normal(tuple(fast.shape)).astype(np.float32)).cuda()
+        fast.backward(g)
+        plain.backward(g)
+        assert torch.allclose(f1.grad, f2.grad, rtol=1e-4, atol=1e-5 * float(f2.grad.abs().max()))
