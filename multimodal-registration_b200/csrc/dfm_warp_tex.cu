@@ -21,7 +21,6 @@
 #include <mutex>
 #include <unordered_map>
 #include <list>
-#include <vector>
 
 #include "dfm_common.cuh"
 #include "dfm_tma.cuh"
@@ -380,9 +379,13 @@ k_warp_tex(const __grid_constant__ TexSet texs, const float *__restrict__ field,
 
 // ------------------------------- host side -----------------------------------------------
 // Texture objects are descriptors over caller memory (no copy).  Creating one costs a few microseconds of host time,
-// so they are cached per (device, base pointer, width, rows); the cache is bounded and evicts the oldest entry.
+// so they are cached per (device, base pointer, width, rows); the cache is bounded (least recently used entries leave).
 // A descriptor only describes an address range: it stays valid (and harmless) after the memory behind it is freed,
 // and a later allocation at the same address with the same geometry is described by the same descriptor.
+// An evicted descriptor may still be referenced by a kernel that has been launched but has not run yet (the library never
+// synchronises), so eviction only moves it to a graveyard of the same capacity; it is destroyed when `cap` further
+// evictions have happened, i.e. after at least `cap` newer descriptors were created -- more launches than a stream can
+// hold pending.  A launch group's descriptors (<= 32) are the most recent entries, so they cannot leave while it is built.
 namespace {
 struct TexKey {
     int dev;
@@ -399,10 +402,15 @@ struct TexCache {
     std::mutex mu;
     std::list<std::pair<TexKey, cudaTextureObject_t>> lru;                  // front = most recent
     std::unordered_map<TexKey, std::list<std::pair<TexKey, cudaTextureObject_t>>::iterator, TexKeyHash> map;
-    static constexpr size_t CAP = 4096;
+    std::list<cudaTextureObject_t> graveyard;                               // evicted, not yet destroyed (front = most recent)
+    size_t cap = 4096;                                                      // DFM_TEX_CACHE_CAP overrides (tests use a small cache)
 };
 TexCache &tex_cache() {
-    static TexCache *c = new TexCache();                                    // leaked on purpose: no destruction order issues at exit
+    static TexCache *c = [] {                                               // leaked on purpose: no destruction order issues at exit
+        TexCache *t = new TexCache();
+        if (const char *e = getenv("DFM_TEX_CACHE_CAP")) t->cap = (size_t)max(2 * W_TEX_PER_LAUNCH, atoi(e));
+        return t;
+    }();
     return *c;
 }
 }  // namespace
@@ -441,10 +449,14 @@ static bool tex_for_volume(const float *base, int Z, int rows, cudaTextureObject
         cudaGetLastError();
         return false;
     }
-    if (c.lru.size() >= TexCache::CAP) {
-        cudaDestroyTextureObject(c.lru.back().second);
+    while (c.lru.size() >= c.cap) {
+        c.graveyard.push_front(c.lru.back().second);
         c.map.erase(c.lru.back().first);
         c.lru.pop_back();
+    }
+    while (c.graveyard.size() > c.cap) {
+        cudaDestroyTextureObject(c.graveyard.back());
+        c.graveyard.pop_back();
     }
     c.lru.emplace_front(key, t);
     c.map[key] = c.lru.begin();
@@ -512,15 +524,17 @@ static int launch_rescale_warp_march(const float *img, const float *half, float 
         cudaFuncSetAttribute(k_rescale_warp_tex<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         configured = true;
     }
-    std::vector<cudaTextureObject_t> all((size_t)B, 0);
-    if (!nearest)
-        for (int b = 0; b < B; ++b)
-            if (!tex_for_volume(img + (size_t)b * Xi * Yi * Zi, Zi, Xi * Yi, &all[(size_t)b])) return DFM_EUNSUPPORTED;
     const uint32_t *bits = reinterpret_cast<const uint32_t *>(img);
     for (int b0 = 0; b0 < B; b0 += W_TEX_PER_LAUNCH) {
         const int nb = min(W_TEX_PER_LAUNCH, B - b0);
         TexSet ts = {};
-        for (int i = 0; i < nb; ++i) ts.t[i] = all[(size_t)(b0 + i)];
+        if (!nearest)
+            for (int i = 0; i < nb; ++i)
+                if (!tex_for_volume(img + (size_t)(b0 + i) * Xi * Yi * Zi, Zi, Xi * Yi, &ts.t[i])) {
+                    // nothing has been launched for this call yet only if this is the first group
+                    DFM_REQUIRE(b0 == 0, DFM_ECUDA, "k_rescale_warp_tex: texture object creation failed after %d items", b0 + i);
+                    return DFM_EUNSUPPORTED;
+                }
         dim3 grid(nzt * nyt, nxt, nb), block((W_NCW + 1) * 32);
 #define DFM_RWT(HFv, NNv) k_rescale_warp_tex<HFv, NNv><<<grid, block, 0, st>>>(tmap, ts, bits, out, cx, cy, cz, Xh, Yh, Zh, X, Y, Z, Xi, Yi, Zi, pre, 1.f, fill, nzt, b0, 0u)
         if (nearest) { if (has_fill) DFM_RWT(true, true); else DFM_RWT(false, true); }
@@ -558,14 +572,15 @@ int launch_warp_tex(const float *img, const float *field, float *out, int B, int
     if (!on || (flags & DFM_LOC_ABSOLUTE) || !tex_volume_ok(img, B, Xi, Yi, Zi)) return DFM_EUNSUPPORTED;
     const int nzt = (Z + 31) / 32, nyt = (Y + 7) / 8, nxt = (X + 1) / 2;
     if ((unsigned long long)nzt * nyt * nxt * ((unsigned long long)nzt * nyt) >= (1ull << 32)) return DFM_EUNSUPPORTED;   // fast_div range
-    std::vector<cudaTextureObject_t> all((size_t)B);
-    for (int b = 0; b < B; ++b)
-        if (!tex_for_volume(img + (size_t)b * Xi * Yi * Zi, Zi, Xi * Yi, &all[(size_t)b])) return DFM_EUNSUPPORTED;
     const FastDiv dz = make_fastdiv((uint32_t)nzt), dyz = make_fastdiv((uint32_t)(nzt * nyt));
     for (int b0 = 0; b0 < B; b0 += W_TEX_PER_LAUNCH) {
         const int nb = min(W_TEX_PER_LAUNCH, B - b0);
         TexSet ts = {};
-        for (int i = 0; i < nb; ++i) ts.t[i] = all[(size_t)(b0 + i)];
+        for (int i = 0; i < nb; ++i)
+            if (!tex_for_volume(img + (size_t)(b0 + i) * Xi * Yi * Zi, Zi, Xi * Yi, &ts.t[i])) {
+                DFM_REQUIRE(b0 == 0, DFM_ECUDA, "k_warp_tex: texture object creation failed after %d items", b0 + i);
+                return DFM_EUNSUPPORTED;
+            }
         dim3 grid((unsigned)(nzt * nyt * nxt), nb, 1), block(256);
 #define DFM_WT(FC, HFv) k_warp_tex<FC, HFv><<<grid, block, 0, st>>>(ts, field, out, Xi, Yi, Zi, X, Y, Z, fill, dz, dyz, b0)
         if (flags & DFM_FIELD_IN_CL) {

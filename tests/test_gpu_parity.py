@@ -521,6 +521,43 @@ def test_fused_rescale_nearest_warp():
     np.testing.assert_array_equal(got, want)
 
 
+def test_texture_descriptor_cache_eviction():
+    """The host-side cache of texture descriptors with a small capacity (own process: the capacity is read when the library
+    loads): hundreds of distinct image buffers cycle through it, every result stays bit-equal to the TMA-brick kernel."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import os, sys
+        import numpy as np, torch
+        sys.path.insert(0, %r)
+        import multimodal_registration_b200 as mrb
+        from multimodal_registration_b200 import ops
+        rng = np.random.default_rng(5)
+        flow = torch.from_numpy((rng.standard_normal((3, 16, 24, 32, 3)) * 2).astype(np.float32)).cuda()
+        half = ops.to_layout(torch.from_numpy((rng.standard_normal((3, 8, 12, 16, 3)) * 1.5).astype(np.float32)).cuda(), 'planar')
+        keep, bad = [], 0   # (planar: the stand-alone up-sampler then runs the same marching arithmetic as the fused kernel)
+        for it in range(120):                               # 360 descriptors through a cache of 64 (+ 64 in the graveyard)
+            img = torch.rand((3, 16, 24, 32, 1), device='cuda')
+            keep.append(img)                                # distinct addresses: nothing is freed
+            a = ops.warp(img, flow)
+            f = ops.rescale_warp(img, half, 2)
+            os.environ['DFM_WARP_TEX'] = '0'
+            b = ops.warp(img, flow)
+            g = ops.warp(img, ops.rescale_dense_transform(half, 2))
+            del os.environ['DFM_WARP_TEX']
+            bad += int(not torch.equal(a, b)) + int(not torch.equal(f, g))
+        # the first buffers' descriptors are long gone: they are re-created on demand
+        bad += int(not torch.equal(ops.warp(keep[0], flow), ops.warp(keep[0].clone(), flow)))
+        torch.cuda.synchronize()
+        print('BAD', bad)
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DFM_TEX_CACHE_CAP='64')
+    if mrb._lib.exact_order():
+        env['DFM_EXACT'] = '1'
+    res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert 'BAD 0' in res.stdout, res.stdout[-500:]
+
+
 def test_fused_texture_gather_is_reproducible():
     """The coarse-plane ring of the fused kernel is released by data-dependent arrivals (a consumer's arrival must not
     overtake its shared loads): many launches at a size with thousands of CTAs give the same bits every time."""
