@@ -55,6 +55,10 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
     labels = [torch.randint(0, C, (B, *FULL, 1), generator=g).float().to(dev) for _ in range(2)]
     flow_full = torch.nn.functional.interpolate(torch.randn(B, 3, 20, 20, 24, generator=g) * 1.5, size=FULL, mode='trilinear',
                                                 align_corners=True).permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    # the flow is what a torch flow convolution emits: NCDHW storage, i.e. this package's "planar" layout of the logical
+    # channels-last tensor (the gradient that comes back in the same layout is taken as is, no layout copy)
+    if not os.environ.get('DFM_TRAIN_FLOW_CL'):
+        flow_full = ops.to_layout(flow_full, 'planar')
     image = torch.rand(B, *FULL, 1, generator=g).to(dev)
     unet_grad = torch.zeros(1446979, device=dev)
 
@@ -79,9 +83,11 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
         # pred = SpatialTransformer('linear')([map_1, flow]): map_1 is the generator's one-hot map, warped from its label map
         # (ops.warp_onehot: the same bits as the generic channels-last warp of the one-hot tensor, 8 bytes gathered per voxel)
         pred = ops.warp_onehot(labels_u8, pos, C) if labels_u8 is not None else ops.warp(onehot_cl, pos)
-        pred.backward(gpred)
+        # the gradient that reaches the flow convolution (autograd.grad: handed on as produced, as it would be to the conv's
+        # backward -- .backward() on a leaf adds AccumulateGrad's layout copy, which is not part of the path)
+        gflow, = torch.autograd.grad(pred, flow, gpred)
         sharding.allreduce_mean_(unet_grad)                       # the step's only collective
-        return flow.grad, y_source
+        return gflow, y_source
 
     for _ in range(warmup):
         step()
