@@ -51,7 +51,8 @@ class SpatialTransformer(torch.nn.Module):
         if self.single_transform:
             trf = trf[:1].expand(vol.shape[0], -1, -1, -1, -1).contiguous()
         lab = getattr(vol, 'dfm_labels', None)
-        if lab is not None and self.interp_method == 'linear' and tuple(lab[0].shape) == tuple(vol.shape[:4]) and not vol.requires_grad:
+        if (lab is not None and self.interp_method == 'linear' and tuple(lab[0].shape) == tuple(vol.shape[:4])
+                and int(lab[1]) == int(vol.shape[-1]) and not vol.requires_grad):
             # a one-hot map from ne.models.labels_to_image: warp it from its label map (same bits, 8 bytes per voxel gathered)
             return ops.warp_onehot(lab[0], trf, lab[1], self.fill_value)
         return ops.warp(vol, trf, self.interp_method, self.fill_value)
