@@ -60,6 +60,7 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
     if not os.environ.get('DFM_TRAIN_FLOW_CL'):
         flow_full = ops.to_layout(flow_full, 'planar')
     image = torch.rand(B, *FULL, 1, generator=g).to(dev)
+    vel_cat, labels_cat = torch.cat(vel, 0), torch.cat(labels, 0)      # the two generators' inputs, drawn into one batch
     unet_grad = torch.zeros(1446979, device=dev)
 
     # harness-only tensors, made once: the one-hot encoding belongs to labels_to_image's intensity model
@@ -71,10 +72,10 @@ def measure(rank, world, dev, items=2, steps=5, warmup=3):
     def step():
         # generators (no gradient)
         with torch.no_grad():
-            maps = []
-            for k in range(2):
-                # VecInt -> RescaleTransform(2) -> nearest warp; the full-resolution field is an intermediate (fused kernel)
-                maps.append(ops.rescale_warp(labels[k], ops.vecint(vel[k], STEPS), 2, 0, 'nearest'))
+            # both generators in one batch of 2 B items: VecInt -> RescaleTransform(2) -> nearest warp; the full-resolution
+            # field is an intermediate (fused kernel)
+            m = ops.rescale_warp(labels_cat, ops.vecint(vel_cat, STEPS), 2, 0, 'nearest')
+            maps = [m[:B], m[B:]]
         flow = flow_full.detach().requires_grad_(True)            # what the flow convolution emits (full res)
         svf = ops.rescale_dense_transform(flow, 0.5)
         pos = ops.rescale_dense_transform(ops.vecint(svf, STEPS), 2)
