@@ -53,6 +53,36 @@ def test_argument_validation_without_gpu():
     assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 1, 0) == 0
 
 
+def test_new_entry_points_validate_without_gpu():
+    """dfm_rescale_warp_nearest_fwd / dfm_warp_onehot_fwd / _bwd reject bad arguments before touching the device, and the
+    Python wrappers refuse CPU tensors (no CPU path)."""
+    lib = _lib.load()
+    null, one, two = ctypes.c_void_p(0), ctypes.c_void_p(512), ctypes.c_void_p(1024)
+    # factor < 1: the fused call only covers the scale-then-resize order
+    rc = lib.dfm_rescale_warp_nearest_fwd(one, one, two, one, one, one, null, 1, 8, 8, 8, 4, 4, 4, 8, 8, 8, 0.5, 0, 0, null)
+    assert rc == -1 and b'factor' in lib.dfm_last_error()
+    # out aliasing img
+    rc = lib.dfm_rescale_warp_nearest_fwd(one, one, one, one, one, one, null, 1, 8, 8, 8, 4, 4, 4, 8, 8, 8, 2.0, 0, 0, null)
+    assert rc == -1 and b'alias' in lib.dfm_last_error()
+    # empty batch is a no-op
+    assert lib.dfm_rescale_warp_nearest_fwd(one, one, two, one, one, one, null, 0, 8, 8, 8, 4, 4, 4, 8, 8, 8, 2.0, 0, 0, null) == 0
+    # one-hot warp: labels are bytes, the label volume needs every axis >= 2, the adjoint's gradient tile bounds C
+    rc = lib.dfm_warp_onehot_fwd(one, one, two, 1, 300, 8, 8, 8, 8, 8, 8, 0, 0.0, 0, null)
+    assert rc == -1 and b'byte' in lib.dfm_last_error()
+    rc = lib.dfm_warp_onehot_fwd(one, one, two, 1, 26, 1, 8, 8, 8, 8, 8, 0, 0.0, 0, null)
+    assert rc == -1 and b'axis' in lib.dfm_last_error()
+    rc = lib.dfm_warp_onehot_bwd(one, one, one, two, 1, 60, 8, 8, 8, 8, 8, 8, 0, 0, null)
+    assert rc == -3 and b'tile' in lib.dfm_last_error()
+    assert lib.dfm_warp_onehot_fwd(one, one, two, 0, 26, 8, 8, 8, 8, 8, 8, 0, 0.0, 0, null) == 0
+    from multimodal_registration_b200 import ops
+    lab = torch.zeros((1, 4, 4, 4), dtype=torch.uint8)
+    fld = torch.zeros((1, 4, 4, 4, 3))
+    with pytest.raises(_lib.DfmError):
+        ops.warp_onehot(lab, fld, 5)
+    with pytest.raises(_lib.DfmError):
+        ops.rescale_warp(torch.zeros((1, 8, 8, 8, 1)), fld, 2, None, 'nearest')
+
+
 def test_coordinate_tables_follow_tf_linspace():
     c = _coords.linspace_tf(80, 160)
     assert c.dtype == np.float32 and c[0] == 0 and c[-1] == 79
