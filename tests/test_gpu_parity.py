@@ -558,6 +558,27 @@ def test_texture_descriptor_cache_eviction():
     assert 'BAD 0' in res.stdout, res.stdout[-500:]
 
 
+def test_texture_kernels_inside_cuda_graph_capture():
+    """Texture descriptors are created on first use; the first use may be inside a stream capture (descriptor creation is not a
+    stream operation, the library relaxes the capture mode around it).  Replays read the current buffer contents."""
+    rng = np.random.default_rng(616)
+    half = dev(smooth_noise(rng, (2, 8, 12, 16, 3), 2.0, smooth=1), 'planar')
+    scan = torch.rand((2, 16, 24, 32, 1), device='cuda')             # a fresh buffer: no descriptor cached for it yet
+    flow = ops.rescale_dense_transform(half, 2)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fused = ops.rescale_warp(scan, half, 2)
+        plain = ops.warp(scan, flow)
+    for _ in range(2):
+        scan.copy_(torch.rand_like(scan))                           # new contents, same address
+        g.replay()
+        torch.cuda.synchronize()
+        with warp_kernel('brick'):
+            want = ops.warp(scan, flow)
+        assert torch.equal(plain, want) and torch.equal(fused, want)
+
+
 def test_fused_texture_gather_is_reproducible():
     """The coarse-plane ring of the fused kernel is released by data-dependent arrivals (a consumer's arrival must not
     overtake its shared loads): many launches at a size with thousands of CTAs give the same bits every time."""
