@@ -188,7 +188,7 @@ def run_own(args):
     mrb._lib.load()
 
     B = args.batch
-    svf_h, img_h = synth_inputs(B, 'cpu', rank)
+    svf_h, img_h = synth_inputs(B, 'cpu', int(os.environ.get('BENCH_SEED', rank)))      # BENCH_SEED: tuning aid (another rank's data on one GPU)
     svf_pin, img_pin = svf_h.pin_memory(), img_h.pin_memory()
     svf, img = svf_pin.to(dev), img_pin.to(dev)
     model = mrb.voxelmorph.networks.VxmDense(FULL, int_steps=INT_STEPS, svf_resolution=2, int_resolution=2)   # fuses rescale+warp at inference

@@ -199,7 +199,9 @@ extern "C" int dfm_field_warp_add(const float *src, const float *own, float *out
 extern "C" size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nsteps, int save_steps) {
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || nsteps <= 0) return 0;
     const size_t one = (size_t)B * 3 * X * Y * Z * sizeof(float);
-    const size_t bound = ((size_t)B * sizeof(float) + 255) / 256 * 256;     // per-item displacement bound (static halo)
+    // per-item displacement maxima: of the first step's output (static halo, adjoint kernel selection) and of the outputs of the
+    // two steps before the last (halo selection of the last two steps)
+    const size_t bound = 3 * (((size_t)B * sizeof(float) + 255) / 256 * 256);
     if (save_steps) return one * (size_t)nsteps + bound;
     return nsteps >= 2 ? one + bound : 0;
 }
@@ -226,14 +228,23 @@ static int ss_step(const float *vin, float *vout, int B, int X, int Y, int Z, fl
 // displacements of the step's input: the last two steps pick the halo-2 or the halo-3 ring PER ITEM on the
 // device (both variants are launched; the CTAs of the one not selected skip the item), earlier steps always
 // run halo 2 (|v| halves with every step back; outliers gather from global memory, so this is only tuning).
+// `meas_in` (nullable, device): max |vin| per item as measured by the previous step -- when given it replaces the doubled bound
+// for the selection; `meas_out` (nullable): this step records max |vout| per item there (zeroed by the caller).
 static int march_step(const float *vin, float *vout, int B, int X, int Y, int Z, float scale, bool in_cl, bool first,
-                      float *absmax, int steps_left, const float *bound, float bscale, cudaStream_t st) {
+                      float *absmax, int steps_left, const float *bound, float bscale, const float *meas_in, float *meas_out,
+                      cudaStream_t st) {
+    // an item runs on the halo-2 ring iff its displacement figure is below the threshold: 3.2 on the doubled bound (loose by
+    // construction), DFM_MARCH_THR_MEAS on the measured maximum
     static const float thr = getenv("DFM_MARCH_THR") ? (float)atof(getenv("DFM_MARCH_THR")) : 3.2f;    // tuning aid
-    if (steps_left >= 2 || !bound)
-        return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 0, nullptr, 0.f, 0.f, 0, st);
-    int rc = launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 0, bound, bscale, thr, 1, st);
+    static const float thr_m = getenv("DFM_MARCH_THR_MEAS") ? (float)atof(getenv("DFM_MARCH_THR_MEAS")) : 3.0f;
+    float *mo = first ? absmax : meas_out;
+    if (steps_left >= 2 || !(bound || meas_in))
+        return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, mo, 0, nullptr, 0.f, 0.f, 0, st);
+    const float *sel = meas_in ? meas_in : bound;
+    const float ss = meas_in ? 1.f : bscale, th = meas_in ? thr_m : thr;
+    int rc = launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, mo, 0, sel, ss, th, 1, st);
     if (rc) return rc;
-    return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, absmax, 1, bound, bscale, thr, 2, st);
+    return launch_ss_march(vin, vout, B, X, Y, Z, scale, in_cl, first, mo, 1, sel, ss, th, 2, st);
 }
 
 extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, int X, int Y, int Z,
@@ -275,7 +286,7 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
             float *vout = (k == nsteps - 1) ? out : work + (size_t)(k + 1) * n;
             unsigned f = (k == nsteps - 1) ? out_cl : 0u;
             rc = DFM_EUNSUPPORTED;
-            if (march && !f) rc = march_step(vin, vout, B, X, Y, Z, 1.f, false, false, nullptr, nsteps - 1 - k, bound, ldexpf(1.f, k), st);
+            if (march && !f) rc = march_step(vin, vout, B, X, Y, Z, 1.f, false, false, nullptr, nsteps - 1 - k, bound, ldexpf(1.f, k), nullptr, nullptr, st);
             if (rc == DFM_EUNSUPPORTED)
                 rc = ss_step(vin, vout, B, X, Y, Z, 1.f, f, nsteps - 1 - k, bound, ldexpf(1.f, k), nullptr, st);
             if (rc) return rc;
@@ -288,10 +299,12 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
     // kernel's static-halo path trusts the bound without a per-voxel check.
     const bool want_bound = (in_cl || march) && nsteps >= 2;
     bool have_bound = false;
+    const size_t bstride = ((size_t)B * sizeof(float) + 255) / 256 * 64;     // floats between the three per-item arrays
     if (want_bound) {
-        cudaError_t e = cudaMemsetAsync(bound, 0, (size_t)B * sizeof(float), st);
+        cudaError_t e = cudaMemsetAsync(bound, 0, 3 * bstride * sizeof(float), st);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "dfm_vecint_fwd: %s", cudaGetErrorString(e));
     }
+    static const bool no_meas = getenv("DFM_MARCH_NO_MEAS") != nullptr;       // tuning aid: doubled bound only
     const float *cur = svf;
     unsigned cur_cl = in_cl;
     for (int k = 0; k < nsteps; ++k) {
@@ -303,7 +316,12 @@ extern "C" int dfm_vecint_fwd(const float *svf, float *out, float *work, int B, 
         const float *bnd = (have_bound && k >= 1) ? bound : nullptr;       // bnd * 2^(k-1) bounds the input of step k
         rc = DFM_EUNSUPPORTED;
         if (march && !(f & DFM_FIELD_OUT_CL)) {
-            rc = march_step(cur, dst, B, X, Y, Z, scale, cur_cl != 0, k == 0, measure, nsteps - 1 - k, bnd, ldexpf(1.f, k - 1), st);
+            // steps nsteps-3 and nsteps-2 record max |out| per item (slots 1 and 2); steps nsteps-2 and nsteps-1 select on them
+            const int left = nsteps - 1 - k;
+            const bool meas_ok = want_bound && !no_meas && nsteps >= 4;
+            float *mout = (meas_ok && k >= 1 && (left == 2 || left == 1)) ? bound + (left == 2 ? 1 : 2) * bstride : nullptr;
+            const float *min_ = (meas_ok && k >= 2 && (left == 1 || left == 0)) ? bound + (left == 1 ? 1 : 2) * bstride : nullptr;
+            rc = march_step(cur, dst, B, X, Y, Z, scale, cur_cl != 0, k == 0, measure, left, bnd, ldexpf(1.f, k - 1), min_, mout, st);
             if (rc == DFM_OK && measure) have_bound = true;
         }
         if (rc == DFM_EUNSUPPORTED && k == 0 && in_cl && !(f & DFM_FIELD_OUT_CL)) {       // channels-last svf: optimistic static brick

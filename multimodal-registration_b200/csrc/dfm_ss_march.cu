@@ -96,7 +96,9 @@ struct MarchRun {
 // bookkeeping, barrier wait / arrive, loop) is shared by VPT voxels and their gathers interleave.
 // IN_CL: 0 = planar source; 1 = channels-last source in 96-float sub-boxes (any Z); 2 = channels-last source as contiguous rows of
 // 3 Z floats through one 5-D box per plane (Z a multiple of 32): corner addressing with immediate offsets like the planar path
-template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST>
+// MEAS: max |out| per batch item goes to absmax (the first step always measures; the two steps before the last measure so that the
+// per-item halo choice of the last two steps rests on the displacements actually present, not on a bound doubled per step)
+template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST, bool MEAS>
 __global__ void __launch_bounds__((TY / VPT * NZW + 1) * 32, march_ctas(TY, H, R, NZW))
 k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ out, int X,
            int Y, int Z, float scale, int nstrips, unsigned long long total, float *__restrict__ absmax, MarchSel sel) {
@@ -121,8 +123,27 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
     __syncthreads();
     const uint32_t full_u = smem_u32(&full[0]), empty_u = smem_u32(&empty[0]);
 
-    uint32_t t = (uint32_t)(total * blockIdx.x / gridDim.x);          // total < 2^32 (host)
-    const uint32_t t1 = (uint32_t)(total * (blockIdx.x + 1) / gridDim.x);
+    // Per-item variant selection (sel.mode): the batch items this launch serves are COMPACTED before the plane-steps are dealt
+    // out, so that a batch split between the two halo variants keeps every CTA of both launches busy (dealing out all items
+    // and skipping the foreign ones left whole CTAs idle: a mixed batch cost up to 15 % of a step).  Up to 64 items: every warp
+    // reads the per-item figures once (lane = item, one ballot per 32 items) and keeps the selection as a 64-bit mask;
+    // larger batches skip as before.
+    auto selected = [&](int b) -> bool {
+        const bool below = __ldg(sel.sel + b) * sel.scale < sel.thr;   // false for NaN
+        return (sel.mode == 1) == below;
+    };
+    const uint32_t per_item = (uint32_t)nstrips * (uint32_t)X;
+    const int nb = (int)(total / per_item);
+    const bool compact = sel.mode != 0 && nb <= 64;
+    unsigned long long mine = total;
+    uint32_t mask_lo = 0, mask_hi = 0;
+    if (compact) {                                                     // reached by every lane of every warp (before the role split)
+        mask_lo = __ballot_sync(0xffffffffu, lane < nb && selected(lane));
+        if (nb > 32) mask_hi = __ballot_sync(0xffffffffu, 32 + lane < nb && selected(32 + lane));
+        mine = (unsigned long long)(__popc(mask_lo) + __popc(mask_hi)) * per_item;
+    }
+    uint32_t t = (uint32_t)(mine * blockIdx.x / gridDim.x);            // total < 2^32 (host)
+    const uint32_t t1 = (uint32_t)(mine * (blockIdx.x + 1) / gridDim.x);
     // next run of this CTA's range (identical in every thread): false when the range is exhausted
     auto next_run = [&](MarchRun &r) -> bool {
         while (t < t1) {
@@ -132,9 +153,11 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
             r.y0 = (int)(item - (uint32_t)r.b * (uint32_t)nstrips) * TY;
             r.xe = (int)min((uint32_t)X, (uint32_t)r.xs + (t1 - t));
             t += (unsigned)(r.xe - r.xs);
-            if (sel.mode) {                                            // per-item variant selection
-                const bool below = __ldg(sel.sel + r.b) * sel.scale < sel.thr;     // false for NaN
-                if ((sel.mode == 1) != below) continue;
+            if (compact) {                                             // r.b counts selected items: map it to the batch index
+                const int nlo = __popc(mask_lo);
+                r.b = r.b < nlo ? (int)__fns(mask_lo, 0, r.b + 1) : 32 + (int)__fns(mask_hi, 0, r.b - nlo + 1);
+            } else if (sel.mode && !selected(r.b)) {
+                continue;
             }
             r.p_first = max(r.xs - H, 0);
             r.p_last = min(r.xe - 1 + H, X - 1);
@@ -206,6 +229,7 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
         int xmh1 = r.xs - H + 1;
         float fx = (float)r.xs;
         int am = 0;                                                    // max |out| as float bits (NaN orders above +inf)
+        float amf = 0.f;
 
         for (int x = r.xs; x < r.xe; ++x) {
             const int need = rq + min(x + H, r.p_last) - r.p_first;
@@ -312,9 +336,11 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                     upk(add2(v0, acc[0]), rA0, rB0);
                     upk(add2(v1, acc[1]), rA1, rB1);
                     upk(add2(v2, acc[2]), rA2, rB2);
-                    if (FIRST)
+                    if (MEAS && FIRST)
                         am = max(max(max(am, __float_as_int(rA0) & 0x7fffffff), max(__float_as_int(rA1) & 0x7fffffff, __float_as_int(rA2) & 0x7fffffff)),
                                  max(__float_as_int(rB0) & 0x7fffffff, max(__float_as_int(rB1) & 0x7fffffff, __float_as_int(rB2) & 0x7fffffff)));
+                    else if (MEAS)      // later steps only steer the halo choice: float max of |.| (one FMNMX per value; a NaN is skipped)
+                        amf = fmaxf(fmaxf(fmaxf(amf, fabsf(rA0)), fmaxf(fabsf(rA1), fabsf(rA2))), fmaxf(fabsf(rB0), fmaxf(fabsf(rB1), fabsf(rB2))));
                     if (ok[0]) { float *o = op[0]; o[0] = rA0; o[N] = rA1; o[2 * (size_t)N] = rA2; }
                     if (ok[1]) { float *o = op[1]; o[0] = rB0; o[N] = rB1; o[2 * (size_t)N] = rB2; }
                     op[0] += XS; op[1] += XS;
@@ -394,8 +420,10 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
                 }
                 if (FIRST) { a[0] = __fmul_rn(scale, a[0]); a[1] = __fmul_rn(scale, a[1]); a[2] = __fmul_rn(scale, a[2]); }
                 const float r0 = __fadd_rn(v0, a[0]), r1 = __fadd_rn(v1, a[1]), r2 = __fadd_rn(v2, a[2]);
-                if (FIRST)
+                if (MEAS && FIRST)
                     am = max(max(am, __float_as_int(r0) & 0x7fffffff), max(__float_as_int(r1) & 0x7fffffff, __float_as_int(r2) & 0x7fffffff));
+                else if (MEAS)
+                    amf = fmaxf(fmaxf(amf, fabsf(r0)), fmaxf(fabsf(r1), fabsf(r2)));
                 if (ok[j]) {
                     float *o = op[j];
                     o[0] = r0; o[N] = r1; o[2 * (size_t)N] = r2;
@@ -425,7 +453,8 @@ k_ss_march(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ s
         const int np = r.p_last - r.p_first + 1;
         rq += np;
         rslot = (rslot + np) % R;
-        if (FIRST && absmax) {
+        if (MEAS && absmax) {
+            if (!FIRST) am = __float_as_int(amf);
             am = __reduce_max_sync(0xffffffffu, am);
             if (lane == 0) atomicMax(reinterpret_cast<int *>(absmax) + r.b, am);
         }
@@ -438,7 +467,7 @@ static int march_cfg_int(const char *name, int dflt) {
     return c ? atoi(c) : dflt;
 }
 
-template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST>
+template <int TY, int VPT, int H, int R, int NZW, int IN_CL, bool FIRST, bool MEAS>
 static int launch_march_t(const float *src, float *out, int B, int X, int Y, int Z, float scale, float *absmax,
                           MarchSel sel, int seglen, cudaStream_t st) {
     constexpr int ROWS = TY + 2 * H, ZP = NZW * 32;
@@ -451,9 +480,9 @@ static int launch_march_t(const float *src, float *out, int B, int X, int Y, int
     if (!enc) return DFM_EUNSUPPORTED;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST, MEAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DFM_REQUIRE(e == cudaSuccess, DFM_ECUDA, "k_ss_march smem attribute: %s", cudaGetErrorString(e));
-        cudaFuncSetAttribute(k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST, MEAS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     // persistent grid: every resident CTA slot gets one contiguous range of plane-steps (at least `seglen` of them)
@@ -468,7 +497,7 @@ static int launch_march_t(const float *src, float *out, int B, int X, int Y, int
     if (total >= (1ull << 32)) return DFM_EUNSUPPORTED;
     const unsigned long long slots = (unsigned long long)sms * march_ctas(TY, H, R, NZW);
     const unsigned grid = (unsigned)max(1ull, min(slots, total / (unsigned)max(seglen, 1)));
-    k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST><<<grid, (TY / VPT * NZW + 1) * 32, smem, st>>>(tmap, src, out, X, Y, Z, scale, nstrip, total, absmax, sel);
+    k_ss_march<TY, VPT, H, R, NZW, IN_CL, FIRST, MEAS><<<grid, (TY / VPT * NZW + 1) * 32, smem, st>>>(tmap, src, out, X, Y, Z, scale, nstrip, total, absmax, sel);
     return check_launch("k_ss_march");
 }
 
@@ -478,11 +507,12 @@ static int launch_march_modes(const float *src, float *out, int B, int X, int Y,
     if (in_cl) {
         if (!first) return DFM_EUNSUPPORTED;
         static const bool no_rows = getenv("DFM_MARCH_NO_CL_ROWS") != nullptr;                       // tuning aid
-        if (Z == NZW * 32 && !no_rows) return launch_march_t<TY, VPT, H, R, NZW, 2, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
-        return launch_march_t<TY, VPT, H, R, NZW, 1, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+        if (Z == NZW * 32 && !no_rows) return launch_march_t<TY, VPT, H, R, NZW, 2, true, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+        return launch_march_t<TY, VPT, H, R, NZW, 1, true, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
     }
-    return first ? launch_march_t<TY, VPT, H, R, NZW, 0, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st)
-                 : launch_march_t<TY, VPT, H, R, NZW, 0, false>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+    if (first) return launch_march_t<TY, VPT, H, R, NZW, 0, true, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
+    return absmax ? launch_march_t<TY, VPT, H, R, NZW, 0, false, true>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st)
+                  : launch_march_t<TY, VPT, H, R, NZW, 0, false, false>(src, out, B, X, Y, Z, scale, absmax, sel, seglen, st);
 }
 
 bool ss_march_eligible(const float *src, int X, int Y, int Z) {

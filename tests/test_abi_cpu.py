@@ -48,8 +48,8 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b'fp32' in lib.dfm_last_error()
     # empty batch is a no-op
     assert lib.dfm_vecint_fwd(one, ctypes.c_void_p(32), null, 0, 4, 4, 4, 7, 0, 0, null) == 0
-    assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 7, 0) == 2 * 3 * 64 * 4 + 256     # ping-pong field + per-item bound
-    assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 7, 1) == 7 * 2 * 3 * 64 * 4 + 256
+    assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 7, 0) == 2 * 3 * 64 * 4 + 768     # ping-pong field + three per-item maxima
+    assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 7, 1) == 7 * 2 * 3 * 64 * 4 + 768
     assert lib.dfm_vecint_workspace_bytes(2, 4, 4, 4, 1, 0) == 0
 
 
