@@ -162,8 +162,9 @@ int dfm_field_warp_add(const float *src, const float *own, float *out,
  *   svf -> out on grid (X,Y,Z), nsteps >= 0.  `work`: caller scratch of
  *   dfm_vecint_workspace_bytes() bytes (planar fp32).  If save_steps != 0, work receives
  *   v_0 .. v_{nsteps-1} (the inputs of every step, v_0 = svf / 2**nsteps), which
- *   dfm_vecint_bwd needs.  The workspace ends with B floats the call uses for a measured
- *   per-item displacement bound (kernel selection on the device, no host synchronisation).
+ *   dfm_vecint_bwd needs.  The workspace ends with three 256-byte aligned arrays of B floats: the
+ *   per-item maximum displacement measured by the first step and by the two steps before the last
+ *   (kernel selection per item on the device, no host synchronisation; dfm_vecint_bwd reads the first).
  * ------------------------------------------------------------------------------------- */
 size_t dfm_vecint_workspace_bytes(int B, int X, int Y, int Z, int nsteps, int save_steps);
 int dfm_vecint_fwd(const float *svf, float *out, float *work,
